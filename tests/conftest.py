@@ -1,0 +1,25 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "k-diffusion-inverse-problems_b200")
+for p in (ROOT, PKG, os.path.join(ROOT, "tests", "golden")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def golden_small():
+    return np.load(os.path.join(ROOT, "tests", "golden", "golden_small.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_ffhq():
+    return np.load(os.path.join(ROOT, "tests", "golden", "golden_ffhq.npz"))

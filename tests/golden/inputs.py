@@ -1,0 +1,67 @@
+"""Seeded synthetic inputs shared by the golden generator and the tests (CPU torch generator, fixed seeds)."""
+import torch
+
+SIGMA_PROBE = torch.tensor([80.0, 33.3, 10.0, 1.5, 0.3, 0.19, 0.05, 0.01, 0.002, 200.0])
+
+# (operator, guidance, x0_cov_type, sigma, extra ConditionDenoiser kwargs)
+GUIDANCE_COMBOS = [
+    ("gaussian_blur", "pgdm", "pgdm", 10.0, {}),
+    ("gaussian_blur", "pgdm", "pgdm", 0.1, {}),
+    ("gaussian_blur", "I", "convert", 10.0, {}),
+    ("gaussian_blur", "I", "convert", 0.1, {}),
+    ("gaussian_blur", "diffpir", "diffpir", 1.0, {"lambda_": 7.0}),
+    ("gaussian_blur", "II", "convert", 0.1, {}),
+    ("gaussian_blur", "I", "tmpd", 0.1, {}),
+    ("inpainting", "pgdm", "pgdm", 10.0, {}),
+    ("inpainting", "I", "convert", 0.1, {}),
+    ("super_resolution", "I", "analytic", 10.0, {}),
+    ("super_resolution", "I", "analytic", 0.1, {}),
+    ("super_resolution", "I", "convert", 0.1, {}),
+    ("motion_blur", "dps", "dps", 10.0, {"zeta": 1.0}),
+    ("motion_blur", "dps", "dps", 0.1, {"zeta": 1.0}),
+    ("super_resolution", "dps", "dps", 1.0, {"zeta": 1.0}),
+]
+
+# (tag, operator, guidance, cov, sampler, n_steps, churn)
+SAMPLER_RUNS = [
+    ("inpaint_pgdm_euler6", "inpainting", "pgdm", "pgdm", "euler", 6, False),
+    ("gauss_pgdm_heun4", "gaussian_blur", "pgdm", "pgdm", "heun", 4, False),
+    ("gauss_pgdm_heun4_churn", "gaussian_blur", "pgdm", "pgdm", "heun", 4, True),
+]
+
+
+def _g(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+def image(size, batch=1, seed=1):
+    """Ground-truth image in [-1, 1] (x0 = rand*2-1)."""
+    return torch.rand(batch, 3, size, size, generator=_g(seed)) * 2 - 1
+
+
+def unet_input(size, batch, seed):
+    return torch.randn(batch, 3, size, size, generator=_g(seed))
+
+
+def unet_seed(shape, seed):
+    return torch.randn(*shape, generator=_g(seed))
+
+
+def xt(size, sigma, seed=21, batch=1):
+    """A noisy iterate x_t = x0' + sigma*n."""
+    g = _g(seed)
+    return (torch.rand(batch, 3, size, size, generator=g) * 2 - 1) * 0.7 + sigma * torch.randn(batch, 3, size, size, generator=g)
+
+
+def xT(size, seed=3, batch=1, sigma_max=80.0):
+    return torch.randn(batch, 3, size, size, generator=_g(seed)) * sigma_max
+
+
+def theta_map(size, seed=5):
+    """A positive per-pixel variance map, like Convert's Eq. 22 output at small sigma."""
+    return torch.rand(1, 3, size, size, generator=_g(seed)) * 0.05 + 1e-4
+
+
+def sub(a):
+    """4x4 spatial subsample used for the 256x256 golden outputs (arrays whose last dim is 256 only)."""
+    return a[..., ::4, ::4] if a.shape[-1] == 256 else a
