@@ -1,0 +1,211 @@
+/* libkdip — C ABI of the B200-native guided-sampling hot path (drop-in boundary).
+ *
+ * Every entry point takes plain device pointers, sizes and a CUDA stream (pass 0 for the legacy default
+ * stream); none allocates device memory after *_create, none synchronises, all are safe under CUDA-graph
+ * capture unless stated.  The caller owns every I/O buffer and workspace.  All image tensors at this boundary
+ * are NCHW contiguous fp32, exactly what the reference's Python passes around.
+ *
+ * Return value: 0 on success, <0 = KDIP_E*; kdip_last_error() returns a thread-local message.
+ *
+ * Each function cites the reference interface (file:line under /root/reference) it replaces.
+ */
+#ifndef KDIP_H_
+#define KDIP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KDIP_OK 0
+#define KDIP_EINVAL (-1)   /* bad argument / unsupported configuration            */
+#define KDIP_ESHAPE (-2)   /* shape not supported by the kernels                   */
+#define KDIP_EALIGN (-3)   /* pointer alignment                                    */
+#define KDIP_ECUDA (-4)    /* CUDA runtime / driver error (message has details)    */
+#define KDIP_ENOTCONV (-5) /* CG hit maxiter (reference: warnings.warn, non-fatal) */
+#define KDIP_ENOMEM (-6)   /* caller workspace too small                           */
+
+typedef void* kdip_stream_t; /* cudaStream_t */
+
+const char* kdip_last_error(void);
+int kdip_version(void);
+/* Device sanity: returns KDIP_OK when the current device is sm_100 (B200); fills sm_count if non-null. */
+int kdip_device_check(int* sm_count);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Sampler elementwise updates — k_diffusion/sampling.py:118-184 (sample_euler / sample_heun), to_d :46-48.
+ * x, denoised, d, noise: [B,3,H,W] fp32, n = B*3*H*W elements.  Sigmas are host scalars (the schedule lives on
+ * the host, sampling.py:17-23), so no device->host sync is needed for the branch decisions.
+ * ------------------------------------------------------------------------------------------------------------ */
+/* x += noise * s_noise * sqrt(sigma_hat^2 - sigma^2)                                  (sampling.py:124-127,165-168) */
+int kdip_churn(float* x, const float* noise, float s_noise, float sigma, float sigma_hat, size_t n, kdip_stream_t s);
+/* d = (x - denoised)/sigma_hat ; x_out = x + d*dt ; d_out may be NULL (Euler)          (sampling.py:129-134,170-179) */
+int kdip_euler_step(const float* x, const float* denoised, float sigma_hat, float dt, float* x_out, float* d_out,
+                    size_t n, kdip_stream_t s);
+/* d2 = (x2 - denoised2)/sigma_next ; x_out = x + (d + d2)/2 * dt                       (sampling.py:180-183) */
+int kdip_heun_step(const float* x, const float* d, const float* x2, const float* denoised2, float sigma_next, float dt,
+                   float* x_out, size_t n, kdip_stream_t s);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * p_mean_variance epilogue + x0-covariance — guided_diffusion/gaussian_diffusion.py:262-276,296-297,305-311,
+ * condition/condition.py:232-248.  Per-image scalar tables (host floats, length B): the caller extracts them
+ * from the float64 schedule at integer t (gaussian_diffusion.py:895-908).
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+  float c_in;          /* 1/sqrt(sigma^2+1)                      k_diffusion/external.py:97-100 */
+  float recip;         /* sqrt(1/abar_t)                          gaussian_diffusion.py:145      */
+  float recipm1;       /* sqrt(1/abar_t - 1)                      gaussian_diffusion.py:146      */
+  float min_log;       /* posterior_log_variance_clipped[t]       :154-158                       */
+  float max_log;       /* log(beta_t)                             :271                           */
+  float post_var;      /* posterior_variance[t]  (Convert Eq.22)  condition.py:244               */
+  float inv_coef1_sq;  /* 1/posterior_mean_coef1[t]^2             condition.py:245               */
+} kdip_pmv_scalars;
+
+/* unet_out [B,6,HW], x [B,3,HW] (UNSCALED x_t; the kernel applies c_in) ->
+ *   x0_mean [B,3,HW] = clamp(recip*c_in*x - recipm1*eps, -1, 1)
+ *   x0_var  [B,3,HW] (may be NULL) = clip((exp(frac*max_log+(1-frac)*min_log) - post_var)*inv_coef1_sq, 1e-6)
+ * sc: device array of B kdip_pmv_scalars. */
+int kdip_pmv_epilogue(const float* unet_out, const float* x, const kdip_pmv_scalars* sc, float* x0_mean, float* x0_var,
+                      int B, int HW, kdip_stream_t s);
+/* VJP seed for the UNet output given v = d(loss)/d(x0_mean): writes seed [B,6,HW] = (-recipm1*m*v, 0) with
+ * m = 1 where the clamp is inactive (x0_mean strictly inside (-1,1) reproduces torch.clamp's gradient), and
+ * direct [B,3,HW] = recip*c_in*m*v (the d/dx of the explicit recip*c_in*x term). */
+int kdip_pmv_vjp_seed(const float* x0_mean, const float* v, const kdip_pmv_scalars* sc, float* seed,
+                      float* direct, int B, int HW, kdip_stream_t s);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Guidance combine — condition/condition.py:131,137,147,156,164,173:
+ *   hat_x0 = clip(x0_mean + coef[b] * (c_in[b]*unet_grad + direct), -1, 1)   (types I / PiGDM / DPS)
+ *   hat_x0 = clip(x0_mean + coef[b] * mat, -1, 1)                            (DiffPIR: pass unet_grad=mat, direct=NULL)
+ * coef, c_in: device arrays of B floats (c_in may be NULL -> 1).
+ * ------------------------------------------------------------------------------------------------------------ */
+int kdip_guidance_combine(const float* x0_mean, const float* unet_grad, const float* direct, const float* coef,
+                          const float* c_in, float* hat_x0, int B, int CHW, kdip_stream_t s);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Inpainting — condition/measurements.py:211-238, condition/condition.py:317-323.
+ * mask: [3,HW] fp32 0/1 shared by the batch (measurements.py:209).
+ * ------------------------------------------------------------------------------------------------------------ */
+/* y = (x + sigma_s*noise) * mask ; noise may be NULL (noiseless)                         measurements.py:211-215 */
+int kdip_inpaint_forward(const float* x, const float* noise, const float* mask, float sigma_s, float* y, int B, int CHW,
+                         kdip_stream_t s);
+/* closed form: mat = (mask*y - mask*x0)/(sigma_s^2 + theta[b]) ; sigma_s already clipped to >=1e-3 by the caller */
+int kdip_inpaint_mat_scalar(const float* y, const float* x0, const float* mask, const float* theta, float sigma_s,
+                            float* mat, int B, int CHW, kdip_stream_t s);
+/* flatten: gather y at mask>0 positions (torch.where order: c,h,w) — idx [M] int32 ascending offsets into CHW  :217-219 */
+int kdip_gather(const float* src, const int32_t* idx, float* dst, int B, int CHW, int M, kdip_stream_t s);
+/* transpose(flatten=True): scatter into zeros                                                                :231-234 */
+int kdip_scatter(const float* src, const int32_t* idx, float* dst, int B, int CHW, int M, kdip_stream_t s);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Implicit-GEMM convolution on the tcgen05 tensor cores (the UNet's conv3x3 / conv1x1 / qkv / proj and their
+ * input-gradients) — replaces cuDNN under guided_diffusion/unet.py:185,211,222,287,295,617.
+ * Activations are bf16 NHWC; weights bf16 [taps*Cout][Cin] (K-major), one row block per tap.
+ * out[n,y,x,:] = bias + residual + sum_seg sum_tap W_seg[tap] . act_seg[n, y+dy(tap), x+dx(tap), :]
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+  const void* act; /* bf16 [N,H,W,C]                         */
+  int C;           /* multiple of 64                          */
+  const void* wgt; /* bf16 [taps*Cout_pad][C]                 */
+  int taps;        /* 9 (3x3, pad 1, tap = ky*3+kx) or 1      */
+} kdip_conv_seg;
+
+typedef struct {
+  int N, H, W;
+  int Cout_pad;  /* GEMM N: multiple of 16 (<=256) or of 64; rows per tap in wgt                 */
+  int Cout;      /* real output channels written (<= Cout_pad)                                   */
+  int nseg;      /* 1..3 K-segments accumulated into the same output (e.g. conv3x3 + 1x1 skip)   */
+  kdip_conv_seg seg[3];
+  const float* bias;    /* [Cout_pad] fp32 or NULL                                               */
+  const void* residual; /* bf16 NHWC with Cout channels or NULL                                  */
+  int res_mode;         /* 0 none, 1 same resolution, 2 avg-pool 2x2 of [N,2H,2W,C], 3 nearest-up of [N,H/2,W/2,C] */
+  void* out;            /* out_mode 0: bf16 [N,H,W,Cout]; 1: fp32 [N,Cout,H,W]                   */
+  int out_mode;
+  float out_scale;      /* multiplies the final value (out_mode 1 only; e.g. c_in for the input-VJP) */
+  float* chan_stats;    /* optional fp32 [N,Cout,2] (sum, sum of squares) accumulated atomically; NULL to skip */
+} kdip_conv_desc;
+
+typedef struct kdip_conv_plan kdip_conv_plan; /* encoded TMA descriptors + launch geometry */
+int kdip_conv_plan_create(const kdip_conv_desc* d, kdip_conv_plan** out);
+int kdip_conv_plan_run(const kdip_conv_plan* p, kdip_stream_t s);
+void kdip_conv_plan_destroy(kdip_conv_plan* p);
+
+/* fp32 OIHW (or [O][I] / [O][I][1]) -> packed bf16 [taps*rows_pad][cols_pad], zero padded.
+ * flip_transpose=0: rows = output channels, cols = input channels (forward operator).
+ * flip_transpose=1: rows = input channels, cols = output channels, taps reversed:
+ *   W'[tap'][ci][co] = W[co][ci][taps-1-tap'] — the input-gradient (dgrad) operator of a stride-1 pad-1 conv. */
+int kdip_pack_conv_weight(const float* w_oihw, int Cout, int Cin, int taps, int rows_pad, int cols_pad,
+                          int flip_transpose, void* dst_bf16, kdip_stream_t s);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * ADM UNet denoiser — guided_diffusion/unet.py:398-668 (UNetModel), built as create_model does
+ * (guided_diffusion/script_util.py:130-184) with condition/diffpir_utils/utils_model.py:353-387 defaults:
+ * resblock_updown, use_scale_shift_norm, learn_sigma (6 output channels), legacy attention order, head width 64.
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+  int image_size;         /* 256 (FFHQ / ImageNet) or 64 (test geometry)                      */
+  int in_channels;        /* 3                                                                */
+  int model_channels;     /* num_channels: 128 (FFHQ), 256 (ImageNet)                         */
+  int out_channels;       /* 6 (learn_sigma)                                                  */
+  int num_res_blocks;     /* 1 (FFHQ), 2 (ImageNet)                                           */
+  int num_head_channels;  /* 64                                                               */
+  int n_mult;             /* levels                                                           */
+  float channel_mult[8];  /* script_util.py:148-160                                           */
+  int n_att;
+  int attention_ds[8];    /* downsample rates with attention, script_util.py:162-164          */
+} kdip_unet_arch;
+
+typedef struct kdip_unet kdip_unet;
+
+/* names[i] / ptrs[i] / numels[i]: the reference state_dict (UNetModel.load_state_dict keys), fp32 tensors resident on
+ * the current device.  The handle packs its own bf16 copies; the caller keeps ownership of the sources.  An optional
+ * pair "out_cov.weight" [6,C,1,1] / "out_cov.bias" [6] enables the DWT-Var covariance head of
+ * k_diffusion/external.py:141,163-165.  Allocates device memory (weights only); synchronises the legacy stream. */
+int kdip_unet_create(const kdip_unet_arch* arch, int n_tensors, const char* const* names, const float* const* ptrs,
+                     const int64_t* numels, kdip_unet** out);
+void kdip_unet_destroy(kdip_unet* u);
+/* Bytes of caller workspace needed for a batch of N images (activations kept for the VJP included). */
+int kdip_unet_workspace_bytes(kdip_unet* u, int N, size_t* bytes);
+/* UNetModel.forward (unet.py:636-668): x [N,3,S,S] fp32 NCHW, multiplied on load by x_scale[n] if non-NULL (c_in of
+ * k_diffusion/external.py:97-100, condition/condition.py:238); t [N] fp32 timesteps (integers for v1, fractional for
+ * v2); out [N,6,S,S] fp32.  cov_out [N,6,S,S] (or NULL) = out_cov(feature) (external.py:163-165).
+ * Activations needed by kdip_unet_vjp stay in `workspace` until the next forward on it. */
+int kdip_unet_forward(kdip_unet* u, const float* x, const float* x_scale, const float* t, int N, float* out,
+                      float* cov_out, void* workspace, size_t ws_bytes, kdip_stream_t s);
+/* Input-VJP of the preceding forward: grad_x [N,3,S,S] = d<seed, out>/d(x*x_scale)  (torch.autograd.grad sites
+ * condition/condition.py:136,146,155,172,269).  seed [N,6,S,S] fp32. */
+int kdip_unet_vjp(kdip_unet* u, const float* seed, int N, float* grad_x, void* workspace, size_t ws_bytes,
+                  kdip_stream_t s);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * UNet building blocks, exported for per-layer parity tests (tests/test_layers_gpu.py).  Activations are bf16 NHWC.
+ * See csrc/unet_kernels.cuh for the full semantics of each argument.
+ * ------------------------------------------------------------------------------------------------------------ */
+int kdip_layer_chan_stats(const void* x, int N, int P, int C, float* stats, kdip_stream_t s);
+int kdip_layer_gn_finalize(const float* stats0, int C0, const float* stats1, int C1, int N, int P, const float* gamma,
+                           const float* beta, const float* film, int film_stride, int film_off, float* ab, float* mr,
+                           kdip_stream_t s);
+int kdip_layer_gn_apply(const void* src0, int C0, const void* src1, int C1, int N, int H, int W, const float* ab,
+                        int act_silu, int resample, void* out, kdip_stream_t s);
+int kdip_layer_gn_bwd(const void* src0, int C0, const void* src1, int C1, int N, int H, int W, const float* ab,
+                      const float* mr, int act_silu, int resample, const void* gy, const void* extra, int extra_mode,
+                      float* red_zeroed, float* k_scratch, void* dst0, void* dst1, kdip_stream_t s);
+int kdip_layer_conv_small_cin(const float* in, const float* in_scale, const float* w_oihw, const float* bias, int N,
+                              int O, int I, int flip, int H, int W, float* w_scratch, void* out, kdip_stream_t s);
+int kdip_layer_time_embed(const float* t, int N, int mc, const float* w1, const float* b1, const float* w2,
+                          const float* b2, float* semb, kdip_stream_t s);
+int kdip_layer_emb_proj(const float* semb, int N, int ted, const float* wall, const float* ball, int R, float* out,
+                        kdip_stream_t s);
+int kdip_layer_attention_fwd(const void* qkv, int N, int T, int heads, void* out, float* lse, kdip_stream_t s);
+int kdip_layer_attention_bwd(const void* qkv, const void* out, const void* d_out, const float* lse, int N, int T,
+                             int heads, void* dqkv, kdip_stream_t s);
+/* fp32 NCHW <-> bf16 NHWC converters (test plumbing and v2 feature export) */
+int kdip_nchw_f32_to_nhwc_bf16(const float* src, int N, int C, int H, int W, void* dst, kdip_stream_t s);
+int kdip_nhwc_bf16_to_nchw_f32(const void* src, int N, int C, int H, int W, float* dst, kdip_stream_t s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KDIP_H_ */

@@ -1,0 +1,426 @@
+// Implicit-GEMM convolution for the ADM UNet on the 5th-gen tensor cores (sm_100a).
+//
+// Replaces the cuDNN/cuBLAS calls under guided_diffusion/unet.py:185,211 (ResBlock conv3x3), :222 (1x1 skip),
+// :287,295 (attention qkv / proj conv1d), :617 (output head) and their input-gradients (autograd sites
+// condition/condition.py:136,146,155,172,269).
+//
+// GEMM view:  D[pixel, co] = sum_seg sum_tap sum_ci  act_seg[pixel + offset(tap), ci] * W_seg[tap][co][ci]
+//   M = 128 output pixels per CTA tile (a TN x TH x TW box of the NHWC activation),
+//   N = BN output channels (16..256), K = 64-channel blocks walked over (segment, tap, channel chunk).
+// Data movement: one elected producer thread issues TMA tile loads — the A box is the *shifted* pixel box of the
+//   tap (out-of-bounds rows/cols are zero-filled by TMA = the conv's zero padding), the B box is BN rows of the
+//   tap's weight slab — into a ring of 128B-swizzled shared-memory stages.
+// Math: one elected thread issues tcgen05.mma (M=128, N=BN, K=16, bf16 x bf16 -> fp32) with the accumulator in
+//   TMEM, double-buffered so the epilogue of tile i overlaps the main loop of tile i+1 (persistent CTAs).
+// Epilogue (4 warps = 128 TMEM lanes): tcgen05.ld -> +bias -> +residual (identity / 2x2 avg-pool / nearest-up
+//   skip paths of unet.py:190-197,257) -> bf16 NHWC or fp32 NCHW store (+ optional per-channel GroupNorm sums).
+#include "kdip_common.cuh"
+
+namespace kdip {
+
+static constexpr int kBlockM = 128;
+static constexpr int kBlockK = 64;                      // bf16 elements = 128 bytes = one swizzle row
+static constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KiB
+static constexpr int kThreads = 256;
+static constexpr int kMaxStages = 8;
+
+struct ConvParams {
+  CUtensorMap mapA[3];
+  CUtensorMap mapB[3];
+  int seg_taps[3];
+  int seg_chunks[3];
+  int nseg;
+  int N, H, W;
+  int TW, TH, TN;
+  int tiles_x, tiles_y, tiles_n, n_tiles, total_tiles;
+  int BN, Cout_pad, Cout;
+  int num_stages;
+  uint32_t idesc;
+  const float* bias;
+  const __nv_bfloat16* residual;
+  int res_mode;
+  void* out;
+  int out_mode;
+  float out_scale;
+  float* chan_stats;
+};
+
+struct TileCoord {
+  int n0, y0, x0, nn0;
+};
+__device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile) {
+  TileCoord t;
+  int nt = tile % p.n_tiles;
+  int mt = tile / p.n_tiles;
+  t.nn0 = nt * p.BN;
+  int tx = mt % p.tiles_x;
+  int r = mt / p.tiles_x;
+  int ty = r % p.tiles_y;
+  int tn = r / p.tiles_y;
+  t.x0 = tx * p.TW;
+  t.y0 = ty * p.TH;
+  t.n0 = tn * p.TN;
+  return t;
+}
+
+__device__ __forceinline__ void load8_bf16(const __nv_bfloat16* p, float (&f)[8]) {
+  uint4 u = *reinterpret_cast<const uint4*>(p);
+  float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment required by the 128B swizzle atoms (TMA destination and UMMA descriptors)
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+
+  const int stage_bytes = kABytes + p.BN * 128;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.num_stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* tmem_full_bar = empty_bar + kMaxStages;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.nseg; ++s) {
+      tma_prefetch_desc(&p.mapA[s]);
+      tma_prefetch_desc(&p.mapB[s]);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.num_stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr_smem, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  int kblocks_total = 0;
+  for (int s = 0; s < p.nseg; ++s) kblocks_total += p.seg_taps[s] * p.seg_chunks[s];
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx_bytes = (uint32_t)stage_bytes;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile);
+        for (int s = 0; s < p.nseg; ++s) {
+          const int taps = p.seg_taps[s];
+          for (int tap = 0; tap < taps; ++tap) {
+            const int dy = (taps == 9) ? (tap / 3 - 1) : 0;
+            const int dx = (taps == 9) ? (tap % 3 - 1) : 0;
+            for (int ch = 0; ch < p.seg_chunks[s]; ++ch) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              uint8_t* a_dst = smem + stage * stage_bytes;
+              uint8_t* b_dst = a_dst + kABytes;
+              mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+              tma_load_4d(a_dst, &p.mapA[s], &full_bar[stage], ch * kBlockK, t.x0 + dx, t.y0 + dy, t.n0);
+              tma_load_2d(b_dst, &p.mapB[s], &full_bar[stage], ch * kBlockK, tap * p.Cout_pad + t.nn0);
+              if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (single thread) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
+        for (int kb = 0; kb < kblocks_total; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
+          const uint64_t a_desc = umma_desc_sw128(a_addr);
+          const uint64_t b_desc = umma_desc_sw128(a_addr + kABytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            // advance 16 bf16 = 32 bytes inside the 128B swizzle atom: +2 in the (addr>>4) field
+            umma_bf16_ss(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), p.idesc, (kb | k) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs retire
+          if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: 4 warps, warp q owns TMEM lanes [32q, 32q+32) =====================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int tw = row % p.TW;
+    const int th = (row / p.TW) % p.TH;
+    const int tn = row / (p.TW * p.TH);
+    const size_t HW = (size_t)p.H * p.W;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile);
+      const int n = t.n0 + tn, y = t.y0 + th, x = t.x0 + tw;
+      const bool valid = (n < p.N) && (y < p.H) && (x < p.W);
+      const size_t pix = ((size_t)n * p.H + y) * p.W + x;
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
+      const int ncols = p.BN < 32 ? p.BN : 32;
+      for (int c0 = 0; c0 < p.BN; c0 += 32) {
+        uint32_t v[32];
+        if (p.BN >= 32) {
+          tmem_ld_32x32(t_row + (uint32_t)c0, v);
+        } else {
+          uint32_t v16[16];
+          tmem_ld_32x16(t_row + (uint32_t)c0, v16);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = v16[j];
+#pragma unroll
+          for (int j = 16; j < 32; ++j) v[j] = 0;
+        }
+        tmem_ld_wait();
+        const int col0 = t.nn0 + c0;
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < ncols) f[j] += __ldg(p.bias + col0 + j);
+        }
+        if (valid && p.res_mode != 0) {
+          // skip path of the ResBlock / attention residual (bf16 NHWC with Cout channels)
+          const int C = p.Cout;
+          if (p.res_mode == 1) {
+            const __nv_bfloat16* r = p.residual + pix * C + col0;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              float r8[8];
+              load8_bf16(r + g * 8, r8);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[g * 8 + j] += r8[j];
+            }
+          } else if (p.res_mode == 2) {
+            // 2x2 average pool of the [N,2H,2W,C] source (Downsample, unet.py:136)
+            const int W2 = p.W * 2;
+            const __nv_bfloat16* r = p.residual + (((size_t)n * (p.H * 2) + 2 * y) * W2 + 2 * x) * C + col0;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              float a8[8], b8[8], c8[8], d8[8];
+              load8_bf16(r + g * 8, a8);
+              load8_bf16(r + C + g * 8, b8);
+              load8_bf16(r + (size_t)W2 * C + g * 8, c8);
+              load8_bf16(r + (size_t)W2 * C + C + g * 8, d8);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[g * 8 + j] += 0.25f * ((a8[j] + b8[j]) + (c8[j] + d8[j]));
+            }
+          } else {
+            // nearest-neighbour x2 of the [N,H/2,W/2,C] source (Upsample, unet.py:107)
+            const int Wh = p.W / 2;
+            const __nv_bfloat16* r = p.residual + (((size_t)n * (p.H / 2) + (y >> 1)) * Wh + (x >> 1)) * C + col0;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              float r8[8];
+              load8_bf16(r + g * 8, r8);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[g * 8 + j] += r8[j];
+            }
+          }
+        }
+        if (valid) {
+          if (p.out_mode == 0) {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.Cout + col0;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint4 u;
+              u.x = pack_bf16(f[g * 8 + 0], f[g * 8 + 1]);
+              u.y = pack_bf16(f[g * 8 + 2], f[g * 8 + 3]);
+              u.z = pack_bf16(f[g * 8 + 4], f[g * 8 + 5]);
+              u.w = pack_bf16(f[g * 8 + 6], f[g * 8 + 7]);
+              *reinterpret_cast<uint4*>(o + g * 8) = u;
+            }
+          } else {
+            float* o = reinterpret_cast<float*>(p.out) + ((size_t)n * p.Cout) * HW + (size_t)y * p.W + x;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.Cout) o[(size_t)(col0 + j) * HW] = f[j] * p.out_scale;
+          }
+        }
+        if (p.chan_stats != nullptr) {
+          // per-(image, channel) sum / sum of squares of the stored value, for the next GroupNorm (nn.py:17-19).
+          // Rows of one warp may span two images only when TN > 1 (8x8 level): reduce per image.
+          const int n_lo = __shfl_sync(0xffffffffu, n, 0);
+          const int n_hi = __shfl_sync(0xffffffffu, n, 31);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float val = valid ? f[j] : 0.f;
+            val = __bfloat162float(__float2bfloat16(val));  // statistics of what is stored
+            if (n_lo == n_hi) {
+              float s1 = warp_sum(val), s2 = warp_sum(val * val);
+              if (lane == 0 && n_lo < p.N) {
+                atomicAdd(p.chan_stats + ((size_t)n_lo * p.Cout + col0 + j) * 2, s1);
+                atomicAdd(p.chan_stats + ((size_t)n_lo * p.Cout + col0 + j) * 2 + 1, s2);
+              }
+            } else if (valid) {
+              atomicAdd(p.chan_stats + ((size_t)n * p.Cout + col0 + j) * 2, val);
+              atomicAdd(p.chan_stats + ((size_t)n * p.Cout + col0 + j) * 2 + 1, val * val);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+struct ConvPlan {
+  ConvParams params;
+  int grid;
+  size_t smem_bytes;
+};
+
+static int pick_bn(int cout_pad) {
+  if (cout_pad == 16 || cout_pad == 32 || cout_pad == 64 || cout_pad == 128 || cout_pad == 256) return cout_pad;
+  if (cout_pad % 256 == 0) return 256;
+  if (cout_pad % 128 == 0) return 128;
+  if (cout_pad % 64 == 0) return 64;
+  return -1;
+}
+
+int conv_plan_build(const kdip_conv_desc* d, ConvPlan* plan) {
+  KDIP_REQUIRE(d != nullptr && plan != nullptr, KDIP_EINVAL, "conv: null descriptor");
+  KDIP_REQUIRE(d->nseg >= 1 && d->nseg <= 3, KDIP_EINVAL, "conv: nseg must be 1..3 (got %d)", d->nseg);
+  KDIP_REQUIRE(d->N > 0 && d->H > 0 && d->W > 0, KDIP_ESHAPE, "conv: bad geometry N=%d H=%d W=%d", d->N, d->H, d->W);
+  ConvParams& p = plan->params;
+  memset(&p, 0, sizeof(p));
+  const int BN = pick_bn(d->Cout_pad);
+  KDIP_REQUIRE(BN > 0, KDIP_ESHAPE, "conv: Cout_pad=%d unsupported (need 16, 32 or a multiple of 64)", d->Cout_pad);
+  KDIP_REQUIRE(d->Cout >= 1 && d->Cout <= d->Cout_pad, KDIP_ESHAPE, "conv: Cout=%d > Cout_pad=%d", d->Cout, d->Cout_pad);
+  KDIP_REQUIRE(d->out_mode == 1 || (d->Cout == d->Cout_pad && d->Cout % 32 == 0), KDIP_ESHAPE,
+               "conv: bf16 NHWC output needs Cout == Cout_pad, multiple of 32 (got %d/%d)", d->Cout, d->Cout_pad);
+  KDIP_REQUIRE(d->res_mode == 0 || (d->residual != nullptr && d->out_mode == 0), KDIP_EINVAL,
+               "conv: residual needs a pointer and bf16 output");
+  KDIP_REQUIRE(d->res_mode != 3 || (d->H % 2 == 0 && d->W % 2 == 0), KDIP_ESHAPE, "conv: nearest-up residual needs even H,W");
+  KDIP_REQUIRE(d->out != nullptr && ((uintptr_t)d->out % 16) == 0, KDIP_EALIGN, "conv: out must be 16B aligned");
+  KDIP_REQUIRE(d->chan_stats == nullptr || d->out_mode == 0, KDIP_EINVAL, "conv: chan_stats only with bf16 output");
+
+  p.N = d->N; p.H = d->H; p.W = d->W;
+  p.TW = d->W >= 16 ? 16 : d->W;
+  KDIP_REQUIRE(kBlockM % p.TW == 0, KDIP_ESHAPE, "conv: W=%d must be >=16 or a power of two", d->W);
+  int rem = kBlockM / p.TW;
+  p.TH = d->H >= rem ? rem : d->H;
+  KDIP_REQUIRE(rem % p.TH == 0, KDIP_ESHAPE, "conv: H=%d must be >=%d or a power of two", d->H, rem);
+  p.TN = rem / p.TH;
+  p.tiles_x = (d->W + p.TW - 1) / p.TW;
+  p.tiles_y = (d->H + p.TH - 1) / p.TH;
+  p.tiles_n = (d->N + p.TN - 1) / p.TN;
+  p.BN = BN;
+  p.n_tiles = d->Cout_pad / BN;
+  p.total_tiles = p.tiles_x * p.tiles_y * p.tiles_n * p.n_tiles;
+  p.Cout_pad = d->Cout_pad;
+  p.Cout = d->Cout;
+  p.nseg = d->nseg;
+  p.idesc = umma_idesc_bf16(kBlockM, BN);
+  p.bias = d->bias;
+  p.residual = reinterpret_cast<const __nv_bfloat16*>(d->residual);
+  p.res_mode = d->res_mode;
+  p.out = d->out;
+  p.out_mode = d->out_mode;
+  p.out_scale = d->out_mode == 1 ? d->out_scale : 1.0f;
+  p.chan_stats = d->chan_stats;
+
+  for (int s = 0; s < d->nseg; ++s) {
+    const kdip_conv_seg& sg = d->seg[s];
+    KDIP_REQUIRE(sg.taps == 9 || sg.taps == 1, KDIP_EINVAL, "conv: taps must be 9 or 1 (got %d)", sg.taps);
+    KDIP_REQUIRE(sg.C > 0 && sg.C % kBlockK == 0, KDIP_ESHAPE, "conv: segment channels %d not a multiple of 64", sg.C);
+    KDIP_REQUIRE(sg.act != nullptr && sg.wgt != nullptr, KDIP_EINVAL, "conv: null segment pointer");
+    KDIP_REQUIRE(((uintptr_t)sg.act % 16) == 0 && ((uintptr_t)sg.wgt % 16) == 0, KDIP_EALIGN, "conv: segment pointers must be 16B aligned");
+    p.seg_taps[s] = sg.taps;
+    p.seg_chunks[s] = sg.C / kBlockK;
+    int rc = encode_tmap_bf16_4d(&p.mapA[s], sg.act, (uint64_t)sg.C, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N, kBlockK,
+                                 (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TN);
+    if (rc != KDIP_OK) return rc;
+    rc = encode_tmap_bf16_2d(&p.mapB[s], sg.wgt, (uint64_t)sg.C, (uint64_t)sg.taps * d->Cout_pad, kBlockK, (uint32_t)BN);
+    if (rc != KDIP_OK) return rc;
+  }
+
+  const int stage_bytes = kABytes + BN * 128;
+  const int budget = 200 * 1024;
+  int stages = budget / stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) stages = 2;
+  p.num_stages = stages;
+  plan->smem_bytes = (size_t)stages * stage_bytes + 1024 /*align slack*/ + (2 * kMaxStages + 4) * 8 + 16;
+  int sms = num_sms();
+  plan->grid = p.total_tiles < sms ? p.total_tiles : sms;
+  return KDIP_OK;
+}
+
+int conv_plan_launch(const ConvPlan* plan, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    KDIP_CUDA(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  conv_gemm_kernel<<<plan->grid, kThreads, plan->smem_bytes, stream>>>(plan->params);
+  KDIP_LAUNCH_CHECK();
+  return KDIP_OK;
+}
+
+ConvPlan* conv_plan_new() { return new ConvPlan(); }
+void conv_plan_free(ConvPlan* p) { delete p; }
+
+}  // namespace kdip
+
+struct kdip_conv_plan {
+  kdip::ConvPlan plan;
+};
+
+extern "C" int kdip_conv_plan_create(const kdip_conv_desc* d, kdip_conv_plan** out) {
+  KDIP_REQUIRE(out != nullptr, KDIP_EINVAL, "conv_plan_create: null out");
+  kdip_conv_plan* p = new kdip_conv_plan();
+  int rc = kdip::conv_plan_build(d, &p->plan);
+  if (rc != KDIP_OK) {
+    delete p;
+    return rc;
+  }
+  *out = p;
+  return KDIP_OK;
+}
+extern "C" int kdip_conv_plan_run(const kdip_conv_plan* p, kdip_stream_t s) {
+  KDIP_REQUIRE(p != nullptr, KDIP_EINVAL, "conv_plan_run: null plan");
+  return kdip::conv_plan_launch(&p->plan, (cudaStream_t)s);
+}
+extern "C" void kdip_conv_plan_destroy(kdip_conv_plan* p) { delete p; }

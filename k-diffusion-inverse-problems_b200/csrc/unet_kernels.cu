@@ -1,0 +1,565 @@
+// Non-GEMM kernels of the ADM UNet forward and input-VJP (all HBM-bound; bf16 NHWC activations, fp32 math):
+//   GroupNorm32 statistics / apply (+SiLU, +FiLM scale-shift, +2x2 avg-pool or nearest-up)   nn.py:17-19, unet.py:237-253
+//   GroupNorm backward (reduce / finalize / apply)                                           autograd of the above
+//   direct 3x3 conv for 3- and 6-channel inputs (first layer, head input-gradient)           unet.py:484,617
+//   timestep embedding + all emb_layers projections                                          nn.py:103-121, unet.py:199-205,473-477
+#include "unet_kernels.cuh"
+
+namespace kdip {
+
+static constexpr float kGnEps = 1e-5f;
+
+struct V8 {
+  float v[8];
+};
+__device__ __forceinline__ V8 ld_bf16x8(const bf16* p) {
+  V8 r;
+  uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+  float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = b.x; r.v[3] = b.y; r.v[4] = c.x; r.v[5] = c.y; r.v[6] = d.x; r.v[7] = d.y;
+  return r;
+}
+__device__ __forceinline__ void st_bf16x8(bf16* p, const V8& r) {
+  uint4 u;
+  u.x = pack_bf16(r.v[0], r.v[1]); u.y = pack_bf16(r.v[2], r.v[3]);
+  u.z = pack_bf16(r.v[4], r.v[5]); u.w = pack_bf16(r.v[6], r.v[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+// pointer to 8 channels starting at concatenated channel c0 of pixel (n, p) in a two-source tensor
+__device__ __forceinline__ const bf16* src_ptr(const bf16* s0, int C0, const bf16* s1, int C1, size_t np, int c0) {
+  return (c0 < C0) ? s0 + np * C0 + c0 : s1 + np * C1 + (c0 - C0);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// per-channel statistics
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void chan_stats_kernel(const bf16* __restrict__ x, int P, int C, int rows_per_block, float* __restrict__ stats) {
+  extern __shared__ float red[];  // [rows][vec*16]
+  const int vec = C >> 3;
+  const int rpp = blockDim.x / vec;  // pixel rows handled per pass
+  const int col = threadIdx.x % vec;
+  const int row = threadIdx.x / vec;
+  const int n = blockIdx.y;
+  const int p0 = blockIdx.x * rows_per_block;
+  const int p1 = min(P, p0 + rows_per_block);
+  float s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+  if (row < rpp) {
+    for (int p = p0 + row; p < p1; p += rpp) {
+      V8 a = ld_bf16x8(x + ((size_t)n * P + p) * C + col * 8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s1[j] += a.v[j]; s2[j] += a.v[j] * a.v[j]; }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { red[(row * vec + col) * 16 + j] = s1[j]; red[(row * vec + col) * 16 + 8 + j] = s2[j]; }
+  }
+  __syncthreads();
+  // one thread per (column, j) sums over rows
+  for (int i = threadIdx.x; i < vec * 16; i += blockDim.x) {
+    float acc = 0.f;
+    for (int r = 0; r < rpp; ++r) acc += red[r * vec * 16 + i];
+    const int c = (i >> 4) * 8 + (i & 7);
+    const int which = (i >> 3) & 1;
+    atomicAdd(stats + ((size_t)n * C + c) * 2 + which, acc);
+  }
+}
+
+int launch_chan_stats(const bf16* x, int N, int P, int C, float* stats, cudaStream_t s) {
+  KDIP_REQUIRE(C % 8 == 0 && C / 8 <= 256, KDIP_ESHAPE, "chan_stats: C=%d unsupported", C);
+  const int vec = C / 8;
+  const int rpp = 256 / vec;
+  int target_blocks = (num_sms() * 4 + N - 1) / N;
+  int rows = (P + target_blocks - 1) / target_blocks;
+  if (rows < rpp * 4) rows = rpp * 4;
+  if (rows > P) rows = P;
+  dim3 grid((P + rows - 1) / rows, N);
+  size_t smem = (size_t)rpp * vec * 16 * sizeof(float);
+  chan_stats_kernel<<<grid, 256, smem, s>>>(x, P, C, rows, stats);
+  KDIP_LAUNCH_CHECK();
+  return KDIP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// GroupNorm finalize: per-channel sums -> per-group mean/rstd -> folded affine (A, B)
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void gn_finalize_kernel(const float* __restrict__ st0, int C0, const float* __restrict__ st1, int C1, int P,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   const float* __restrict__ film, int film_stride, int film_off, float* __restrict__ ab,
+                                   float* __restrict__ mr) {
+  __shared__ float g_mean[32], g_rstd[32];
+  const int n = blockIdx.x;
+  const int C = C0 + C1;
+  const int cpg = C / 32;
+  if (threadIdx.x < 32) {
+    const int g = threadIdx.x;
+    double S1 = 0.0, S2 = 0.0;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+      const float* p = (c < C0) ? st0 + ((size_t)n * C0 + c) * 2 : st1 + ((size_t)n * C1 + (c - C0)) * 2;
+      S1 += (double)p[0];
+      S2 += (double)p[1];
+    }
+    const double cnt = (double)cpg * (double)P;
+    const double mean = S1 / cnt;
+    double var = S2 / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)kGnEps));
+    g_mean[g] = (float)mean;
+    g_rstd[g] = rstd;
+    mr[((size_t)n * 32 + g) * 2] = (float)mean;
+    mr[((size_t)n * 32 + g) * 2 + 1] = rstd;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    float w = gamma[c], b = beta[c];
+    float A = w * g_rstd[g];
+    float B = b - g_mean[g] * A;
+    if (film != nullptr) {
+      const float sc = film[(size_t)n * film_stride + film_off + c];
+      const float sh = film[(size_t)n * film_stride + film_off + C + c];
+      A = A * (1.f + sc);
+      B = B * (1.f + sc) + sh;
+    }
+    ab[((size_t)n * C + c) * 2] = A;
+    ab[((size_t)n * C + c) * 2 + 1] = B;
+  }
+}
+
+int launch_gn_finalize(const float* stats0, int C0, const float* stats1, int C1, int N, int P, const float* gamma,
+                       const float* beta, const float* film, int film_stride, int film_off, float* ab, float* mr, cudaStream_t s) {
+  KDIP_REQUIRE((C0 + C1) % 32 == 0, KDIP_ESHAPE, "gn_finalize: channels %d not divisible by 32 groups", C0 + C1);
+  gn_finalize_kernel<<<N, 256, 0, s>>>(stats0, C0, stats1, C1, P, gamma, beta, film, film_stride, film_off, ab, mr);
+  KDIP_LAUNCH_CHECK();
+  return KDIP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// GroupNorm apply (+SiLU, + resample)
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ V8 affine_act(const V8& x, const float* __restrict__ abp, int act_silu) {
+  V8 r;
+  const float4* q = reinterpret_cast<const float4*>(abp);
+  float4 a0 = __ldg(q), a1 = __ldg(q + 1), a2 = __ldg(q + 2), a3 = __ldg(q + 3);
+  const float A[8] = {a0.x, a0.z, a1.x, a1.z, a2.x, a2.z, a3.x, a3.z};
+  const float B[8] = {a0.y, a0.w, a1.y, a1.w, a2.y, a2.w, a3.y, a3.w};
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float u = A[j] * x.v[j] + B[j];
+    r.v[j] = act_silu ? silu_f(u) : u;
+  }
+  return r;
+}
+
+__global__ void gn_apply_kernel(const bf16* __restrict__ s0, int C0, const bf16* __restrict__ s1, int C1, int N, int H, int W,
+                                const float* __restrict__ ab, int act_silu, int resample, bf16* __restrict__ out) {
+  const int C = C0 + C1;
+  const int vec = C >> 3;
+  const int Ho = resample == RS_AVGPOOL2 ? H / 2 : (resample == RS_NEAREST_UP2 ? H * 2 : H);
+  const int Wo = resample == RS_AVGPOOL2 ? W / 2 : (resample == RS_NEAREST_UP2 ? W * 2 : W);
+  const size_t total = (size_t)N * Ho * Wo * vec;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int v = (int)(i % vec);
+    const size_t po = i / vec;
+    const int xo = (int)(po % Wo);
+    const int yo = (int)((po / Wo) % Ho);
+    const int n = (int)(po / ((size_t)Wo * Ho));
+    const int c0 = v * 8;
+    const float* abp = ab + ((size_t)n * C + c0) * 2;
+    V8 r;
+    if (resample == RS_NONE) {
+      r = affine_act(ld_bf16x8(src_ptr(s0, C0, s1, C1, ((size_t)n * H + yo) * W + xo, c0)), abp, act_silu);
+    } else if (resample == RS_NEAREST_UP2) {
+      r = affine_act(ld_bf16x8(src_ptr(s0, C0, s1, C1, ((size_t)n * H + (yo >> 1)) * W + (xo >> 1), c0)), abp, act_silu);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r.v[j] = 0.f;
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          V8 t = affine_act(ld_bf16x8(src_ptr(s0, C0, s1, C1, ((size_t)n * H + 2 * yo + dy) * W + 2 * xo + dx, c0)), abp, act_silu);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) r.v[j] += t.v[j];
+        }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r.v[j] *= 0.25f;
+    }
+    st_bf16x8(out + po * C + c0, r);
+  }
+}
+
+static inline int ew_blocks(size_t total, int threads) {
+  size_t b = (total + threads - 1) / threads;
+  size_t cap = (size_t)num_sms() * 16;
+  return (int)(b < cap ? (b ? b : 1) : cap);
+}
+
+int launch_gn_apply(const bf16* src0, int C0, const bf16* src1, int C1, int N, int H, int W, const float* ab, int act_silu,
+                    int resample, bf16* out, cudaStream_t s) {
+  KDIP_REQUIRE(C0 % 8 == 0 && C1 % 8 == 0, KDIP_ESHAPE, "gn_apply: channels must be multiples of 8");
+  KDIP_REQUIRE(resample != RS_AVGPOOL2 || (H % 2 == 0 && W % 2 == 0), KDIP_ESHAPE, "gn_apply: avg-pool needs even H, W");
+  const int Ho = resample == RS_AVGPOOL2 ? H / 2 : (resample == RS_NEAREST_UP2 ? H * 2 : H);
+  const int Wo = resample == RS_AVGPOOL2 ? W / 2 : (resample == RS_NEAREST_UP2 ? W * 2 : W);
+  size_t total = (size_t)N * Ho * Wo * ((C0 + C1) / 8);
+  gn_apply_kernel<<<ew_blocks(total, 256), 256, 0, s>>>(src0, C0, src1, C1, N, H, W, ab, act_silu, resample, out);
+  KDIP_LAUNCH_CHECK();
+  return KDIP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// GroupNorm backward
+// ---------------------------------------------------------------------------------------------------------------------
+// g_u at input pixel (n,y,x), channels c0..c0+7: resample^T(g_y) * act'(u)
+__device__ __forceinline__ V8 grad_u(const V8& xv, const float* __restrict__ abp, int act_silu, int resample,
+                                     const bf16* __restrict__ gy, int n, int y, int x, int H, int W, int C, int c0) {
+  V8 g;
+  if (resample == RS_NONE) {
+    g = ld_bf16x8(gy + (((size_t)n * H + y) * W + x) * C + c0);
+  } else if (resample == RS_AVGPOOL2) {
+    g = ld_bf16x8(gy + (((size_t)n * (H / 2) + (y >> 1)) * (W / 2) + (x >> 1)) * C + c0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g.v[j] *= 0.25f;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g.v[j] = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        V8 t = ld_bf16x8(gy + (((size_t)n * (2 * H) + 2 * y + dy) * (2 * W) + 2 * x + dx) * C + c0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g.v[j] += t.v[j];
+      }
+  }
+  if (act_silu) {
+    const float4* q = reinterpret_cast<const float4*>(abp);
+    float4 a0 = __ldg(q), a1 = __ldg(q + 1), a2 = __ldg(q + 2), a3 = __ldg(q + 3);
+    const float A[8] = {a0.x, a0.z, a1.x, a1.z, a2.x, a2.z, a3.x, a3.z};
+    const float B[8] = {a0.y, a0.w, a1.y, a1.w, a2.y, a2.w, a3.y, a3.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g.v[j] *= dsilu_f(A[j] * xv.v[j] + B[j]);
+  }
+  return g;
+}
+
+__global__ void gn_bwd_reduce_kernel(const bf16* __restrict__ s0, int C0, const bf16* __restrict__ s1, int C1, int H, int W,
+                                     const float* __restrict__ ab, int act_silu, int resample, const bf16* __restrict__ gy,
+                                     int rows_per_block, float* __restrict__ red_out) {
+  extern __shared__ float red[];
+  const int C = C0 + C1;
+  const int vec = C >> 3;
+  const int rpp = blockDim.x / vec;
+  const int col = threadIdx.x % vec;
+  const int row = threadIdx.x / vec;
+  const int n = blockIdx.y;
+  const int P = H * W;
+  const int p0 = blockIdx.x * rows_per_block;
+  const int p1 = min(P, p0 + rows_per_block);
+  float r1[8], r2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) r1[j] = r2[j] = 0.f;
+  if (row < rpp) {
+    const int c0 = col * 8;
+    const float* abp = ab + ((size_t)n * C + c0) * 2;
+    for (int p = p0 + row; p < p1; p += rpp) {
+      const int y = p / W, x = p % W;
+      V8 xv = ld_bf16x8(src_ptr(s0, C0, s1, C1, (size_t)n * P + p, c0));
+      V8 g = grad_u(xv, abp, act_silu, resample, gy, n, y, x, H, W, C, c0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { r1[j] += g.v[j]; r2[j] += g.v[j] * xv.v[j]; }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { red[(row * vec + col) * 16 + j] = r1[j]; red[(row * vec + col) * 16 + 8 + j] = r2[j]; }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < vec * 16; i += blockDim.x) {
+    float acc = 0.f;
+    for (int r = 0; r < rpp; ++r) acc += red[r * vec * 16 + i];
+    const int c = (i >> 4) * 8 + (i & 7);
+    const int which = (i >> 3) & 1;
+    atomicAdd(red_out + ((size_t)n * C + c) * 2 + which, acc);
+  }
+}
+
+int launch_gn_bwd_reduce(const bf16* src0, int C0, const bf16* src1, int C1, int N, int H, int W, const float* ab, int act_silu,
+                         int resample, const bf16* gy, float* red, cudaStream_t s) {
+  const int C = C0 + C1;
+  KDIP_REQUIRE(C % 8 == 0 && C / 8 <= 256 && C0 % 8 == 0, KDIP_ESHAPE, "gn_bwd_reduce: C=%d unsupported", C);
+  const int vec = C / 8, rpp = 256 / vec, P = H * W;
+  int target_blocks = (num_sms() * 4 + N - 1) / N;
+  int rows = (P + target_blocks - 1) / target_blocks;
+  if (rows < rpp * 4) rows = rpp * 4;
+  if (rows > P) rows = P;
+  dim3 grid((P + rows - 1) / rows, N);
+  size_t smem = (size_t)rpp * vec * 16 * sizeof(float);
+  gn_bwd_reduce_kernel<<<grid, 256, smem, s>>>(src0, C0, src1, C1, H, W, ab, act_silu, resample, gy, rows, red);
+  KDIP_LAUNCH_CHECK();
+  return KDIP_OK;
+}
+
+__global__ void gn_bwd_finalize_kernel(const float* __restrict__ red, const float* __restrict__ ab, const float* __restrict__ mr,
+                                       int C, int P, float* __restrict__ k) {
+  __shared__ float c1s[32], c2s[32];
+  const int n = blockIdx.x;
+  const int cpg = C / 32;
+  if (threadIdx.x < 32) {
+    const int g = threadIdx.x;
+    const float mean = mr[((size_t)n * 32 + g) * 2], rstd = mr[((size_t)n * 32 + g) * 2 + 1];
+    double a1 = 0.0, a2 = 0.0;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+      const double w = (double)ab[((size_t)n * C + c) * 2] / (double)rstd;   // gamma*(1+scale)
+      const double R1 = red[((size_t)n * C + c) * 2], R2 = red[((size_t)n * C + c) * 2 + 1];
+      a1 += w * R1;
+      a2 += w * (double)rstd * (R2 - (double)mean * R1);                      // sum g_xhat * xhat
+    }
+    const double m = (double)cpg * (double)P;
+    c1s[g] = (float)(a1 / m);
+    c2s[g] = (float)(a2 / m);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const float mean = mr[((size_t)n * 32 + g) * 2], rstd = mr[((size_t)n * 32 + g) * 2 + 1];
+    float* kp = k + ((size_t)n * C + c) * 4;
+    kp[0] = ab[((size_t)n * C + c) * 2];                       // k0 = A_c
+    kp[1] = -rstd * c1s[g] + rstd * rstd * mean * c2s[g];      // k1
+    kp[2] = -rstd * rstd * c2s[g];                             // k2
+    kp[3] = 0.f;
+  }
+}
+
+int launch_gn_bwd_finalize(const float* red, const float* ab, const float* mr, const float* /*gamma*/, int N, int C, int P,
+                           const float* /*film*/, int /*film_stride*/, int /*film_off*/, float* k, cudaStream_t s) {
+  gn_bwd_finalize_kernel<<<N, 256, 0, s>>>(red, ab, mr, C, P, k);
+  KDIP_LAUNCH_CHECK();
+  return KDIP_OK;
+}
+
+__global__ void gn_bwd_apply_kernel(const bf16* __restrict__ s0, int C0, const bf16* __restrict__ s1, int C1, int N, int H, int W,
+                                    const float* __restrict__ ab, const float* __restrict__ k, int act_silu, int resample,
+                                    const bf16* __restrict__ gy, const bf16* __restrict__ extra, int extra_mode,
+                                    bf16* __restrict__ d0, bf16* __restrict__ d1) {
+  const int C = C0 + C1;
+  const int vec = C >> 3;
+  const size_t total = (size_t)N * H * W * vec;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int v = (int)(i % vec);
+    const size_t np = i / vec;
+    const int x = (int)(np % W);
+    const int y = (int)((np / W) % H);
+    const int n = (int)(np / ((size_t)W * H));
+    const int c0 = v * 8;
+    const float* abp = ab + ((size_t)n * C + c0) * 2;
+    V8 xv = ld_bf16x8(src_ptr(s0, C0, s1, C1, np, c0));
+    V8 g = grad_u(xv, abp, act_silu, resample, gy, n, y, x, H, W, C, c0);
+    const float4* kq = reinterpret_cast<const float4*>(k + ((size_t)n * C + c0) * 4);
+    V8 r;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float4 kk = __ldg(kq + j);
+      r.v[j] = kk.x * g.v[j] + kk.y + kk.z * xv.v[j];
+    }
+    if (extra_mode == 1) {
+      V8 e = ld_bf16x8(extra + np * C + c0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r.v[j] += e.v[j];
+    } else if (extra_mode == 2) {
+      V8 e = grad_u(xv, abp, 0, resample, extra, n, y, x, H, W, C, c0);   // plain resample^T, no activation factor
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r.v[j] += e.v[j];
+    }
+    bf16* dst = (c0 < C0) ? d0 + np * C0 + c0 : d1 + np * C1 + (c0 - C0);
+    st_bf16x8(dst, r);
+  }
+}
+
+int launch_gn_bwd_apply(const bf16* src0, int C0, const bf16* src1, int C1, int N, int H, int W, const float* ab,
+                        const float* k, int act_silu, int resample, const bf16* gy, const bf16* extra, int extra_mode,
+                        bf16* dst0, bf16* dst1, cudaStream_t s) {
+  KDIP_REQUIRE(C0 % 8 == 0 && C1 % 8 == 0, KDIP_ESHAPE, "gn_bwd_apply: channels must be multiples of 8");
+  KDIP_REQUIRE(extra_mode == 0 || extra != nullptr, KDIP_EINVAL, "gn_bwd_apply: extra_mode set without tensor");
+  size_t total = (size_t)N * H * W * ((C0 + C1) / 8);
+  gn_bwd_apply_kernel<<<ew_blocks(total, 256), 256, 0, s>>>(src0, C0, src1, C1, N, H, W, ab, k, act_silu, resample, gy, extra,
+                                                            extra_mode, dst0, dst1);
+  KDIP_LAUNCH_CHECK();
+  return KDIP_OK;
+}
+
+__global__ void axpy_f32_kernel(float* __restrict__ y, const float* __restrict__ x, float alpha, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) y[i] += alpha * x[i];
+}
+int launch_axpy_f32(float* y, const float* x, float alpha, int n, cudaStream_t s) {
+  axpy_f32_kernel<<<(n + 255) / 256, 256, 0, s>>>(y, x, alpha, n);
+  KDIP_LAUNCH_CHECK();
+  return KDIP_OK;
+}
+
+__global__ void add_bf16_kernel(bf16* __restrict__ a, const bf16* __restrict__ b, size_t n8) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+    V8 x = ld_bf16x8(a + i * 8), y = ld_bf16x8(b + i * 8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x.v[j] += y.v[j];
+    st_bf16x8(a + i * 8, x);
+  }
+}
+int launch_add_bf16(bf16* a, const bf16* b, size_t n, cudaStream_t s) {
+  KDIP_REQUIRE(n % 8 == 0, KDIP_ESHAPE, "add_bf16: n must be a multiple of 8");
+  add_bf16_kernel<<<ew_blocks(n / 8, 256), 256, 0, s>>>(a, b, n / 8);
+  KDIP_LAUNCH_CHECK();
+  return KDIP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// direct 3x3 conv for tiny channel counts on the input side
+// ---------------------------------------------------------------------------------------------------------------------
+template <int CIN>
+__global__ void conv_small_cin_kernel(const float* __restrict__ in, const float* __restrict__ in_scale, const float* __restrict__ w,
+                                      const float* __restrict__ bias, int N, int H, int W, int Cout, bf16* __restrict__ out) {
+  extern __shared__ float ws[];  // [9*CIN][Cout]
+  for (int i = threadIdx.x; i < 9 * CIN * Cout; i += blockDim.x) ws[i] = w[i];
+  __syncthreads();
+  const int tpp = Cout >> 3;              // threads per pixel
+  const int ppb = blockDim.x / tpp;       // pixels per block
+  const int sub = threadIdx.x % tpp;
+  const int pl = threadIdx.x / tpp;
+  if (pl >= ppb) return;
+  const size_t HW = (size_t)H * W;
+  const size_t total = (size_t)N * HW;
+  const int co0 = sub * 8;
+  for (size_t pix = (size_t)blockIdx.x * ppb + pl; pix < total; pix += (size_t)gridDim.x * ppb) {
+    const int n = (int)(pix / HW);
+    const int y = (int)((pix % HW) / W), x = (int)(pix % W);
+    const float sc = in_scale ? __ldg(in_scale + n) : 1.f;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = bias ? __ldg(bias + co0 + j) : 0.f;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+      if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+#pragma unroll
+      for (int ci = 0; ci < CIN; ++ci) {
+        const float v = __ldg(in + ((size_t)n * CIN + ci) * HW + (size_t)yy * W + xx) * sc;
+        const float4* wp = reinterpret_cast<const float4*>(ws + (tap * CIN + ci) * Cout + co0);
+        const float4 w0 = wp[0], w1 = wp[1];
+        acc[0] += v * w0.x; acc[1] += v * w0.y; acc[2] += v * w0.z; acc[3] += v * w0.w;
+        acc[4] += v * w1.x; acc[5] += v * w1.y; acc[6] += v * w1.z; acc[7] += v * w1.w;
+      }
+    }
+    V8 r;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r.v[j] = acc[j];
+    st_bf16x8(out + pix * Cout + co0, r);
+  }
+}
+
+int launch_conv_small_cin(const float* in, const float* in_scale, const float* w, const float* bias, int N, int CIN, int H,
+                          int W, int Cout, bf16* out, cudaStream_t s) {
+  KDIP_REQUIRE(CIN == 3 || CIN == 6, KDIP_ESHAPE, "conv_small_cin: CIN must be 3 or 6 (got %d)", CIN);
+  KDIP_REQUIRE(Cout % 8 == 0 && Cout <= 256 && 256 % (Cout / 8) == 0, KDIP_ESHAPE, "conv_small_cin: Cout=%d unsupported", Cout);
+  const int ppb = 256 / (Cout / 8);
+  size_t total = (size_t)N * H * W;
+  size_t blocks = (total + ppb - 1) / ppb;
+  size_t cap = (size_t)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  size_t smem = (size_t)9 * CIN * Cout * sizeof(float);
+  if (CIN == 3) {
+    conv_small_cin_kernel<3><<<(int)blocks, 256, smem, s>>>(in, in_scale, w, bias, N, H, W, Cout, out);
+  } else {
+    static bool attr = false;
+    if (!attr) {
+      KDIP_CUDA(cudaFuncSetAttribute(conv_small_cin_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+      attr = true;
+    }
+    conv_small_cin_kernel<6><<<(int)blocks, 256, smem, s>>>(in, in_scale, w, bias, N, H, W, Cout, out);
+  }
+  KDIP_LAUNCH_CHECK();
+  return KDIP_OK;
+}
+
+__global__ void pack_small_kernel(const float* __restrict__ w, int O, int I, int flip, float* __restrict__ dst) {
+  const int CIN = flip ? O : I, Cout = flip ? I : O;
+  const int total = 9 * CIN * Cout;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int co = i % Cout, ci = (i / Cout) % CIN, tap = i / (Cout * CIN);
+    float v;
+    if (!flip) v = w[((size_t)co * I + ci) * 9 + tap];          // w[o=co][i=ci][tap]
+    else v = w[((size_t)ci * I + co) * 9 + (8 - tap)];          // w[o=ci][i=co][8-tap]
+    dst[i] = v;
+  }
+}
+int launch_pack_small(const float* w_oihw, int O, int I, int flip, float* dst, cudaStream_t s) {
+  pack_small_kernel<<<64, 256, 0, s>>>(w_oihw, O, I, flip, dst);
+  KDIP_LAUNCH_CHECK();
+  return KDIP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// timestep embedding
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void time_embed_kernel(const float* __restrict__ t, int mc, const float* __restrict__ w1, const float* __restrict__ b1,
+                                  const float* __restrict__ w2, const float* __restrict__ b2, float* __restrict__ semb) {
+  extern __shared__ float sm[];  // e0[mc] | h1[4mc]
+  float* e0 = sm;
+  float* h1 = sm + mc;
+  const int n = blockIdx.x;
+  const int ted = 4 * mc, half = mc / 2;
+  const float tv = t[n];
+  for (int k = threadIdx.x; k < mc; k += blockDim.x) {
+    const int kk = k < half ? k : k - half;
+    const float f = expf(-logf(10000.f) * (float)kk / (float)half);
+    const float a = tv * f;
+    e0[k] = k < half ? cosf(a) : sinf(a);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int j = warp; j < ted; j += nw) {
+    float acc = 0.f;
+    for (int k = lane; k < mc; k += 32) acc += __ldg(w1 + (size_t)j * mc + k) * e0[k];
+    acc = warp_sum(acc);
+    if (lane == 0) h1[j] = silu_f(acc + b1[j]);
+  }
+  __syncthreads();
+  for (int j = warp; j < ted; j += nw) {
+    float acc = 0.f;
+    for (int k = lane; k < ted; k += 32) acc += __ldg(w2 + (size_t)j * ted + k) * h1[k];
+    acc = warp_sum(acc);
+    if (lane == 0) semb[(size_t)n * ted + j] = silu_f(acc + b2[j]);
+  }
+}
+int launch_time_embed(const float* t, int N, int mc, const float* w1, const float* b1, const float* w2, const float* b2,
+                      float* semb, cudaStream_t s) {
+  KDIP_REQUIRE(mc % 2 == 0, KDIP_ESHAPE, "time_embed: model_channels must be even");
+  time_embed_kernel<<<N, 512, (size_t)5 * mc * sizeof(float), s>>>(t, mc, w1, b1, w2, b2, semb);
+  KDIP_LAUNCH_CHECK();
+  return KDIP_OK;
+}
+
+__global__ void emb_proj_kernel(const float* __restrict__ semb, int N, int ted, const float* __restrict__ wall,
+                                const float* __restrict__ ball, int R, float* __restrict__ out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (r >= R) return;
+  float wreg[32];
+  const int per = ted / 32;  // <= 32
+#pragma unroll
+  for (int i = 0; i < 32; ++i) wreg[i] = (i < per) ? __ldg(wall + (size_t)r * ted + i * 32 + lane) : 0.f;
+  const float b = ball[r];
+  for (int n = 0; n < N; ++n) {
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (i < per) acc += wreg[i] * __ldg(semb + (size_t)n * ted + i * 32 + lane);
+    acc = warp_sum(acc);
+    if (lane == 0) out[(size_t)n * R + r] = acc + b;
+  }
+}
+int launch_emb_proj(const float* semb, int N, int ted, const float* wall, const float* ball, int R, float* out, cudaStream_t s) {
+  KDIP_REQUIRE(ted % 32 == 0 && ted <= 1024, KDIP_ESHAPE, "emb_proj: time_embed_dim=%d unsupported", ted);
+  emb_proj_kernel<<<(R + 7) / 8, 256, 0, s>>>(semb, N, ted, wall, ball, R, out);
+  KDIP_LAUNCH_CHECK();
+  return KDIP_OK;
+}
+
+}  // namespace kdip

@@ -1,0 +1,100 @@
+"""Device-side ADM UNet handle (libkdip kdip_unet_*), the engine behind guided_diffusion.unet.UNetModel.
+
+Reference: guided_diffusion/unet.py:398-668 (module), guided_diffusion/script_util.py:130-184 (construction),
+condition/diffpir_utils/utils_model.py:353-387 (hyper-parameter defaults).
+"""
+import ctypes
+
+import torch
+
+from ._lib import UNetArch, check, lib, ptr, stream_ptr
+
+
+def channel_mult_for(image_size):
+    """script_util.py:148-160."""
+    return {512: (0.5, 1, 1, 2, 2, 4, 4), 256: (1, 1, 2, 2, 4, 4), 128: (1, 1, 2, 3, 4), 64: (1, 2, 3, 4)}[image_size]
+
+
+class UNetEngine:
+    """Owns the packed weights (inside libkdip) and the activation workspace (a torch uint8 tensor)."""
+
+    def __init__(self, state_dict, image_size=256, num_channels=128, num_res_blocks=1, attention_resolutions="16",
+                 num_head_channels=64, channel_mult=None, out_cov=None, device="cuda"):
+        if not torch.cuda.is_available():
+            raise RuntimeError("kdip.UNetEngine needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.device = torch.device(device)
+        mult = tuple(channel_mult) if channel_mult else channel_mult_for(image_size)
+        att = tuple(image_size // int(r) for r in str(attention_resolutions).split(","))
+        arch = UNetArch()
+        arch.image_size, arch.in_channels, arch.model_channels, arch.out_channels = image_size, 3, num_channels, 6
+        arch.num_res_blocks, arch.num_head_channels = num_res_blocks, num_head_channels
+        arch.n_mult = len(mult)
+        for i, m in enumerate(mult):
+            arch.channel_mult[i] = float(m)
+        arch.n_att = len(att)
+        for i, d in enumerate(att):
+            arch.attention_ds[i] = int(d)
+        self.arch = arch
+        self.image_size = image_size
+        tensors = {k: v.detach().to(self.device, torch.float32).contiguous() for k, v in state_dict.items()}
+        if out_cov is not None:   # OpenAIDenoiserV2.out_cov (k_diffusion/external.py:141)
+            tensors["out_cov.weight"] = out_cov[0].detach().to(self.device, torch.float32).contiguous()
+            tensors["out_cov.bias"] = out_cov[1].detach().to(self.device, torch.float32).contiguous()
+        self.has_cov = out_cov is not None
+        names = list(tensors.keys())
+        n = len(names)
+        c_names = (ctypes.c_char_p * n)(*[s.encode() for s in names])
+        c_ptrs = (ctypes.c_void_p * n)(*[tensors[s].data_ptr() for s in names])
+        c_numel = (ctypes.c_int64 * n)(*[tensors[s].numel() for s in names])
+        h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            check(lib.kdip_unet_create(ctypes.byref(arch), n, c_names, c_ptrs, c_numel, ctypes.byref(h)))
+        self._h = h
+        self._ws = None
+        self._ws_N = 0
+        self._fwd_N = 0
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            lib.kdip_unet_destroy(h)
+            self._h = None
+
+    def workspace_bytes(self, N):
+        b = ctypes.c_size_t()
+        check(lib.kdip_unet_workspace_bytes(self._h, N, ctypes.byref(b)))
+        return b.value
+
+    def _workspace(self, N):
+        if self._ws is None or self._ws_N != N:
+            self._ws = None
+            self._ws = torch.empty(self.workspace_bytes(N) + 256, dtype=torch.uint8, device=self.device)
+            self._ws_N = N
+        off = (-self._ws.data_ptr()) % 256
+        return ctypes.c_void_p(self._ws.data_ptr() + off), self._ws.numel() - 256
+
+    def forward(self, x, t, x_scale=None, out=None, want_cov=False):
+        """x [N,3,S,S] fp32 cuda, t [N] (any numeric dtype) -> out [N,6,S,S] fp32 (and cov [N,6,S,S])."""
+        N = x.shape[0]
+        x = x.contiguous().float()
+        t = t.to(self.device, torch.float32).contiguous()
+        if x_scale is not None:
+            x_scale = x_scale.to(self.device, torch.float32).contiguous()
+        if out is None:
+            out = torch.empty(N, 6, x.shape[2], x.shape[3], device=self.device, dtype=torch.float32)
+        cov = torch.empty_like(out) if want_cov else None
+        ws, ws_bytes = self._workspace(N)
+        check(lib.kdip_unet_forward(self._h, ptr(x), ptr(x_scale), ptr(t), N, ptr(out), ptr(cov), ws, ws_bytes, stream_ptr()))
+        self._fwd_N = N
+        return (out, cov) if want_cov else out
+
+    def vjp(self, seed, out=None):
+        """seed [N,6,S,S] fp32 -> d<seed, unet_out>/d(unet_input) [N,3,S,S] fp32 for the preceding forward."""
+        N = seed.shape[0]
+        assert N == self._fwd_N, "vjp must follow forward with the same batch"
+        seed = seed.contiguous().float()
+        if out is None:
+            out = torch.empty(N, 3, seed.shape[2], seed.shape[3], device=self.device, dtype=torch.float32)
+        ws, ws_bytes = self._workspace(N)
+        check(lib.kdip_unet_vjp(self._h, ptr(seed), N, ptr(out), ws, ws_bytes, stream_ptr()))
+        return out

@@ -1,0 +1,141 @@
+"""tcgen05 implicit-GEMM conv (csrc/conv_gemm.cu) vs torch conv2d on the same bf16-rounded operands (fp32 math).
+Tolerance: the kernel accumulates in fp32 and stores bf16 -> relative error <= 2^-8 of the output scale."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1.0 / 128  # bf16 store (2^-9 relative) + accumulation-order differences, relative to max |out|
+
+
+def _mk(N, C, H, W, seed):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return torch.randn(N, C, H, W, device="cuda", generator=g)
+
+
+def _bf(x):
+    return x.to(torch.bfloat16).float()
+
+
+CASES = [
+    # N, H, W, Cin, Cout, taps
+    (2, 16, 16, 64, 64, 9),
+    (1, 32, 32, 128, 128, 9),
+    (2, 8, 8, 128, 256, 9),      # 8x8 level: two images per 128-pixel tile
+    (1, 8, 8, 64, 64, 9),        # N=1 with TN=2: out-of-bounds image in the TMA box
+    (3, 16, 16, 192, 64, 1),     # 1x1, K = 3 chunks
+    (2, 16, 16, 64, 576, 1),     # qkv-like: 9 N-tiles of 64
+    (1, 64, 64, 128, 128, 9),    # many tiles per CTA? (32 tiles) + persistent loop
+    (4, 32, 32, 256, 512, 9),    # BN=256, 2 N-tiles, deep K
+    (2, 32, 32, 320, 192, 9),    # non power-of-two channel counts (tiny config)
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "x".join(map(str, c)))
+def test_conv_plain(case):
+    from gpu_util import pack_weight, run_conv, to_nchw_f32, to_nhwc_bf16, relerr
+    N, H, W, Ci, Co, taps = case
+    k = 3 if taps == 9 else 1
+    x = _mk(N, Ci, H, W, 1)
+    w = _mk(Co, Ci, k, k, 2) / (Ci * taps) ** 0.5
+    b = _mk(1, Co, 1, 1, 3).flatten()
+    wp, _ = pack_weight(w)
+    out = run_conv([(to_nhwc_bf16(x), wp, taps)], N, H, W, Co, bias=b)
+    ref = F.conv2d(_bf(x), _bf(w), b, padding=k // 2)
+    got = to_nchw_f32(out)
+    assert torch.isfinite(got).all(), "NaN left in output: some pixels/channels were never written"
+    e = relerr(got, ref)
+    print(f"conv {case}: rel err {e:.3e}")
+    assert e < TOL
+
+
+def test_conv_dgrad_matches_autograd():
+    """flip_transpose packing = input-gradient of the conv (condition/condition.py:172 autograd site)."""
+    from gpu_util import pack_weight, run_conv, to_nchw_f32, to_nhwc_bf16, relerr
+    N, H, W, Ci, Co = 2, 16, 16, 128, 64
+    x = _mk(N, Ci, H, W, 1).requires_grad_()
+    w = _mk(Co, Ci, 3, 3, 2) / (Ci * 9) ** 0.5
+    g = _mk(N, Co, H, W, 4)
+    y = F.conv2d(x, _bf(w), padding=1)
+    (gx,) = torch.autograd.grad(y, x, _bf(g))
+    wd, _ = pack_weight(w, flip=True)
+    out = run_conv([(to_nhwc_bf16(g), wd, 9)], N, H, W, Ci)
+    e = relerr(to_nchw_f32(out), gx)
+    print(f"dgrad rel err {e:.3e}")
+    assert e < TOL
+
+
+@pytest.mark.parametrize("mode", [1, 2, 3])
+def test_conv_residual_modes(mode):
+    """identity / avg-pool / nearest-up skip paths of ResBlock (unet.py:190-197,257) fused in the epilogue."""
+    from gpu_util import pack_weight, run_conv, to_nchw_f32, to_nhwc_bf16, relerr
+    N, H, W, C = 2, 16, 16, 64
+    x = _mk(N, C, H, W, 1)
+    w = _mk(C, C, 3, 3, 2) / (C * 9) ** 0.5
+    rs = {1: (H, W), 2: (2 * H, 2 * W), 3: (H // 2, W // 2)}[mode]
+    r = _mk(N, C, rs[0], rs[1], 5)
+    wp, _ = pack_weight(w)
+    out = run_conv([(to_nhwc_bf16(x), wp, 9)], N, H, W, C, residual=to_nhwc_bf16(r), res_mode=mode)
+    rr = _bf(r)
+    rr = {1: rr, 2: F.avg_pool2d(rr, 2), 3: F.interpolate(rr, scale_factor=2, mode="nearest")}[mode]
+    ref = F.conv2d(_bf(x), _bf(w), padding=1) + rr
+    e = relerr(to_nchw_f32(out), ref)
+    print(f"residual mode {mode}: rel err {e:.3e}")
+    assert e < TOL
+
+
+def test_conv_three_segments():
+    """conv3x3(a2) + 1x1 skip over two concatenated sources accumulated in one TMEM tile (unet.py:222,257,662)."""
+    from gpu_util import pack_weight, run_conv, to_nchw_f32, to_nhwc_bf16, relerr
+    N, H, W, Co, C0, C1 = 2, 16, 16, 128, 192, 64
+    a2, s0, s1 = _mk(N, Co, H, W, 1), _mk(N, C0, H, W, 2), _mk(N, C1, H, W, 3)
+    w2 = _mk(Co, Co, 3, 3, 4) / (Co * 9) ** 0.5
+    ws = _mk(Co, C0 + C1, 1, 1, 5) / (C0 + C1) ** 0.5
+    b = _mk(1, Co, 1, 1, 6).flatten()
+    segs = [(to_nhwc_bf16(a2), pack_weight(w2)[0], 9),
+            (to_nhwc_bf16(s0), pack_weight(ws, ci_off=0, ci_sub=C0)[0], 1),
+            (to_nhwc_bf16(s1), pack_weight(ws, ci_off=C0, ci_sub=C1)[0], 1)]
+    out = run_conv(segs, N, H, W, Co, bias=b)
+    ref = F.conv2d(_bf(a2), _bf(w2), b, padding=1) + F.conv2d(torch.cat([_bf(s0), _bf(s1)], 1), _bf(ws))
+    e = relerr(to_nchw_f32(out), ref)
+    print(f"3-segment rel err {e:.3e}")
+    assert e < TOL
+
+
+@pytest.mark.parametrize("cout", [6, 3])
+def test_conv_small_cout_fp32_nchw(cout):
+    """output head (128 -> 6, unet.py:617) and first-layer input-gradient (C -> 3): N padded to 16, fp32 NCHW store."""
+    from gpu_util import pack_weight, run_conv, to_nhwc_bf16, relerr
+    N, H, W, Ci = 2, 32, 32, 128
+    x = _mk(N, Ci, H, W, 1)
+    w = _mk(cout, Ci, 3, 3, 2) / (Ci * 9) ** 0.5
+    b = _mk(1, cout, 1, 1, 3).flatten()
+    wp, _ = pack_weight(w)
+    out = run_conv([(to_nhwc_bf16(x), wp, 9)], N, H, W, cout, bias=b, out_mode=1, out_scale=0.5)
+    ref = 0.5 * F.conv2d(_bf(x), _bf(w), b, padding=1)
+    assert torch.isfinite(out).all()
+    e = relerr(out, ref)
+    print(f"small-cout {cout}: rel err {e:.3e}")
+    assert e < 1e-4          # fp32 store: only accumulation order differs
+
+
+def test_conv_chan_stats():
+    from gpu_util import pack_weight, run_conv, to_nchw_f32, to_nhwc_bf16
+    N, H, W, C = 3, 8, 8, 64   # TN=2 path: rows of a warp span two images
+    x = _mk(N, C, H, W, 1)
+    w = _mk(C, C, 3, 3, 2) / (C * 9) ** 0.5
+    stats = torch.zeros(N, C, 2, device="cuda")
+    out = run_conv([(to_nhwc_bf16(x), pack_weight(w)[0], 9)], N, H, W, C, stats=stats)
+    got = to_nchw_f32(out)
+    s1, s2 = got.sum((2, 3)), (got * got).sum((2, 3))
+    assert torch.allclose(stats[..., 0], s1, rtol=1e-3, atol=1e-2)
+    assert torch.allclose(stats[..., 1], s2, rtol=1e-3, atol=1e-2)
+
+
+def test_conv_rejects_bad_shapes():
+    from gpu_util import pack_weight, run_conv, to_nhwc_bf16
+    x = _mk(1, 48, 16, 16, 1)     # 48 channels: not a multiple of 64
+    w = _mk(64, 48, 3, 3, 2)
+    with pytest.raises(ValueError):
+        run_conv([(to_nhwc_bf16(x), pack_weight(w)[0], 9)], 1, 16, 16, 64)

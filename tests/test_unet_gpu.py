@@ -1,0 +1,81 @@
+"""Whole-UNet parity: CUDA engine (bf16 tensor-core GEMMs, fp32 accumulate/statistics) vs the fp32 oracle.
+
+Stated tolerance: max |err| <= 3e-2 of the output scale and relative L2 <= 1.5e-2 for the
+forward; 5e-2 / 3e-2 for the input-VJP (two passes through the bf16 network)."""
+import numpy as np
+import pytest
+import torch
+
+import inputs as I
+
+pytestmark = pytest.mark.gpu
+
+
+def _errs(got, ref):
+    got, ref = got.float().cpu(), ref.float().cpu()
+    return ((got - ref).abs().max() / ref.abs().max()).item(), ((got - ref).norm() / ref.norm()).item()
+
+
+@pytest.fixture(scope="module")
+def tiny_engine():
+    from oracle import unet_ref
+    from kdip.unet import UNetEngine
+    cfg = unet_ref.tiny_config()
+    sd = unet_ref.init_state_dict(cfg, seed=0)
+    eng = UNetEngine(sd, image_size=64, num_channels=64, num_res_blocks=1, attention_resolutions="16,8")
+    return cfg, sd, eng
+
+
+def test_tiny_unet_forward_vjp(tiny_engine, golden_small):
+    from oracle import unet_ref
+    cfg, sd, eng = tiny_engine
+    x = I.unet_input(64, batch=2, seed=11)
+    t = torch.tensor([37, 801])
+    out = eng.forward(x.cuda(), t.cuda())
+    ref = torch.from_numpy(golden_small["tiny.out"])            # reference's own output (pinned oracle agrees)
+    e_max, e_l2 = _errs(out, ref)
+    print(f"tiny unet fwd: max-rel {e_max:.3e} l2-rel {e_l2:.3e}")
+    assert torch.isfinite(out).all()
+    assert e_max < 3e-2 and e_l2 < 1.5e-2
+    v = I.unet_seed(out.shape, seed=12)
+    gx = eng.vjp(v.cuda())
+    e_max, e_l2 = _errs(gx, torch.from_numpy(golden_small["tiny.vjp"]))
+    print(f"tiny unet vjp: max-rel {e_max:.3e} l2-rel {e_l2:.3e}")
+    assert e_max < 5e-2 and e_l2 < 3e-2
+    # fractional timesteps (v2 path)
+    out = eng.forward(x.cuda(), torch.tensor([12.25, 640.5]).cuda())
+    e_max, e_l2 = _errs(out, torch.from_numpy(golden_small["tiny.out_fract"]))
+    print(f"tiny unet fwd (fractional t): max-rel {e_max:.3e} l2-rel {e_l2:.3e}")
+    assert e_max < 3e-2 and e_l2 < 1.5e-2
+
+
+def test_tiny_unet_batch_independence_and_scale(tiny_engine):
+    """Images are independent units: batch of 5 == five batches of 1; x_scale == pre-scaling."""
+    cfg, sd, eng = tiny_engine
+    x = I.unet_input(64, batch=5, seed=31).cuda()
+    t = torch.tensor([5, 100, 400, 700, 999]).cuda()
+    sc = torch.tensor([1.0, 0.5, 0.1, 0.05, 0.0125]).cuda()
+    full = eng.forward(x, t, x_scale=sc).clone()
+    for b in range(5):
+        one = eng.forward((x[b:b + 1] * sc[b]).contiguous(), t[b:b + 1])
+        e_max, _ = _errs(one, full[b:b + 1])
+        assert e_max < 2e-2, (b, e_max)   # bf16 network: different tile/stat accumulation order only
+
+
+def test_ffhq_unet_forward(golden_ffhq):
+    from oracle import unet_ref
+    from kdip.unet import UNetEngine
+    cfg = unet_ref.ffhq_config()
+    sd = unet_ref.init_state_dict(cfg, seed=0)
+    cs = float(sum(v.double().sum() for v in sd.values()))
+    assert abs(cs - golden_ffhq["ffhq.sd_checksum"][0]) < 1e-6, "synthetic weights differ from the golden run"
+    eng = UNetEngine(sd, image_size=256, num_channels=128, num_res_blocks=1, attention_resolutions="16")
+    sigma = 1.5
+    xt = I.xt(256, sigma, seed=21)
+    c_in = 1 / (sigma ** 2 + 1) ** 0.5
+    t = torch.from_numpy(golden_ffhq["ffhq.t"])
+    out = eng.forward(xt.cuda(), t.cuda(), x_scale=torch.tensor([c_in]).cuda())
+    ref = torch.from_numpy(golden_ffhq["ffhq.unet_out"].astype(np.float32))
+    e_max, e_l2 = _errs(out, ref)
+    print(f"ffhq unet fwd: max-rel {e_max:.3e} l2-rel {e_l2:.3e}")
+    assert e_max < 3e-2 and e_l2 < 1.5e-2
