@@ -3,6 +3,9 @@
 // its VJP seed, guidance combine (condition.py:131-173) and the inpainting operator / closed-form solve
 // (measurements.py:211-238, condition.py:317-323).  All fp32, float4-vectorised, grid = k * #SMs, no smem needed
 // (every element is touched once — see DESIGN.md for bytes per element of each kernel).
+// Compiled without FMA contraction: the reference evaluates these expressions as separately rounded ATen mul / add
+// kernels, and the mask / inpainting ops are held to bit-exactness against it.
+// NVCC_FLAGS: -fmad=false
 #include "kdip_common.cuh"
 
 namespace kdip {

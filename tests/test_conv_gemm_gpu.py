@@ -47,6 +47,14 @@ def test_conv_plain(case):
     assert torch.isfinite(got).all(), "NaN left in output: some pixels/channels were never written"
     e = relerr(got, ref)
     print(f"conv {case}: rel err {e:.3e}")
+    if not e < TOL:   # failure forensics: where is it wrong?
+        bad = ((got - ref).abs() > TOL * ref.abs().max())
+        print("  bad fraction", bad.float().mean().item())
+        print("  bad per image", bad.float().mean((1, 2, 3)).tolist())
+        print("  bad per channel block of 16", bad.float().mean((0, 2, 3)).view(-1, 16).mean(1).tolist()[:16])
+        print("  bad per row", bad.float().mean((0, 1, 3)).tolist()[:32])
+        print("  bad per col", bad.float().mean((0, 1, 2)).tolist()[:32])
+        print("  sample got/ref", got.flatten()[:8].tolist(), ref.flatten()[:8].tolist())
     assert e < TOL
 
 

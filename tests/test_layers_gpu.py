@@ -68,8 +68,9 @@ def test_groupnorm_forward_backward(C0, C1, rs, silu, film):
     kk = torch.empty(N, C, 4, device="cuda")
     d0 = torch.empty(N, H, W, C0, dtype=torch.bfloat16, device="cuda")
     d1 = torch.empty(N, H, W, max(C1, 8), dtype=torch.bfloat16, device="cuda")
-    check(lib.kdip_layer_gn_bwd(ptr(s0), C0, ptr(s1), C1, N, H, W, ptr(ab), ptr(mr), silu, rs, ptr(to_nhwc_bf16(gy)),
-                                ptr(to_nhwc_bf16(extra)), 1, ptr(red), ptr(kk), ptr(d0), ptr(d1) if C1 else None, st))
+    gy_n, extra_n = to_nhwc_bf16(gy), to_nhwc_bf16(extra)   # keep references: ptr() does not own the tensor
+    check(lib.kdip_layer_gn_bwd(ptr(s0), C0, ptr(s1), C1, N, H, W, ptr(ab), ptr(mr), silu, rs, ptr(gy_n),
+                                ptr(extra_n), 1, ptr(red), ptr(kk), ptr(d0), ptr(d1) if C1 else None, st))
     got = to_nchw_f32(d0)
     if C1:
         got = torch.cat([got, to_nchw_f32(d1)[:, :C1]], 1)
@@ -102,8 +103,8 @@ def test_attention_forward_backward(T, heads, N):
     ga = _mk(N, C, T, seed=2)
     (gq,) = torch.autograd.grad(a, qkv_b, _bf(ga))
     dqkv = torch.empty(N, T, 3 * C, dtype=torch.bfloat16, device="cuda")
-    check(lib.kdip_layer_attention_bwd(ptr(mine_in), ptr(out), ptr(ga.permute(0, 2, 1).contiguous().to(torch.bfloat16)),
-                                       ptr(lse), N, T, heads, ptr(dqkv), st))
+    ga_n = ga.permute(0, 2, 1).contiguous().to(torch.bfloat16)
+    check(lib.kdip_layer_attention_bwd(ptr(mine_in), ptr(out), ptr(ga_n), ptr(lse), N, T, heads, ptr(dqkv), st))
     e = relerr(dqkv.float().permute(0, 2, 1), gq)
     print(f"attn bwd T={T}: rel err {e:.3e}")
     assert e < 2 * TOL

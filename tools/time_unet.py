@@ -1,0 +1,31 @@
+"""Quick device timing of the FFHQ UNet forward / input-VJP (synthetic weights).  Usage: python tools/time_unet.py [B] [iters]"""
+import os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "k-diffusion-inverse-problems_b200")]
+import torch
+from oracle import unet_ref
+from kdip.unet import UNetEngine
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+iters = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+cfg = unet_ref.ffhq_config()
+sd = unet_ref.init_state_dict(cfg, seed=0)
+eng = UNetEngine(sd)
+print("workspace GB", eng.workspace_bytes(B) / 1e9)
+x = torch.randn(B, 3, 256, 256, device="cuda")
+t = torch.full((B,), 500.0, device="cuda")
+seed = torch.randn(B, 6, 256, 256, device="cuda")
+out = torch.empty(B, 6, 256, 256, device="cuda")
+g = torch.empty(B, 3, 256, 256, device="cuda")
+for _ in range(2):
+    eng.forward(x, t, out=out); eng.vjp(seed, out=g)
+torch.cuda.synchronize()
+e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+tf = tb = 0.0
+for _ in range(iters):
+    e[0].record(); eng.forward(x, t, out=out); e[1].record(); eng.vjp(seed, out=g); e[2].record()
+    torch.cuda.synchronize()
+    tf += e[0].elapsed_time(e[1]); tb += e[1].elapsed_time(e[2])
+tf /= iters; tb /= iters
+fl = unet_ref.unet_flops(cfg) * B
+print(f"B={B}: fwd {tf:.2f} ms ({fl/tf/1e9:.1f} TFLOP/s)  vjp {tb:.2f} ms ({fl/tb/1e9:.1f} TFLOP/s)  fwd+vjp {tf+tb:.2f} ms -> {B/(tf+tb)*1000/199:.3f} img/s @199 evals")
