@@ -31,6 +31,8 @@ typedef void* kdip_stream_t; /* cudaStream_t */
 
 const char* kdip_last_error(void);
 int kdip_version(void);
+/* Number of CUDA kernels this library has launched in the process so far (bench.py reports the delta as gpu_launches). */
+unsigned long long kdip_launch_count(void);
 /* Device sanity: returns KDIP_OK when the current device is sm_100 (B200); fills sm_count if non-null. */
 int kdip_device_check(int* sm_count);
 
@@ -60,12 +62,12 @@ typedef struct {
   float min_log;       /* posterior_log_variance_clipped[t]       :154-158                       */
   float max_log;       /* log(beta_t)                             :271                           */
   float post_var;      /* posterior_variance[t]  (Convert Eq.22)  condition.py:244               */
-  float inv_coef1_sq;  /* 1/posterior_mean_coef1[t]^2             condition.py:245               */
+  float coef1_sq;      /* posterior_mean_coef1[t]^2 (fp32 square) condition.py:245               */
 } kdip_pmv_scalars;
 
 /* unet_out [B,6,HW], x [B,3,HW] (UNSCALED x_t; the kernel applies c_in) ->
  *   x0_mean [B,3,HW] = clamp(recip*c_in*x - recipm1*eps, -1, 1)
- *   x0_var  [B,3,HW] (may be NULL) = clip((exp(frac*max_log+(1-frac)*min_log) - post_var)*inv_coef1_sq, 1e-6)
+ *   x0_var  [B,3,HW] (may be NULL) = clip((exp(frac*max_log+(1-frac)*min_log) - post_var)/coef1_sq, 1e-6)
  * sc: device array of B kdip_pmv_scalars. */
 int kdip_pmv_epilogue(const float* unet_out, const float* x, const kdip_pmv_scalars* sc, float* x0_mean, float* x0_var,
                       int B, int HW, kdip_stream_t s);
@@ -84,6 +86,16 @@ int kdip_pmv_vjp_seed(const float* x0_mean, const float* v, const kdip_pmv_scala
 int kdip_guidance_combine(const float* x0_mean, const float* unet_grad, const float* direct, const float* coef,
                           const float* c_in, float* hat_x0, int B, int CHW, kdip_stream_t s);
 
+/* out = a[b]*x + c[b]*y, per-image device scalars, no clipping (y, c may be NULL).  TMPD covariance
+ * sigma^2 * grad_x sum(x0_mean) = (sigma^2 c_in) * unet_grad + sigma^2 * direct                 condition.py:268-269 */
+int kdip_lincomb(const float* x, const float* y, const float* a, const float* c, float* out, int B, int CHW, kdip_stream_t s);
+
+/* v2 (DWT-Var) epilogue — condition/condition.py:287-300, k_diffusion/external.py:161-169:
+ *   x0_mean = unet_out[:, :3]*c_out + x, c_out = -sigma[b];  x0_var = exp(cov_out[:, :3])*c_out^2 ;
+ *   theta0_var = exp(cov_out[:, 3:])*c_out^2 (both NULL to skip; cov_out may then be NULL).  sigma: device [B]. */
+int kdip_v2_epilogue(const float* unet_out, const float* cov_out, const float* x, const float* sigma, float* x0_mean,
+                     float* x0_var, float* theta0_var, int B, int HW, kdip_stream_t s);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Inpainting — condition/measurements.py:211-238, condition/condition.py:317-323.
  * mask: [3,HW] fp32 0/1 shared by the batch (measurements.py:209).
@@ -98,6 +110,65 @@ int kdip_inpaint_mat_scalar(const float* y, const float* x0, const float* mask, 
 int kdip_gather(const float* src, const int32_t* idx, float* dst, int B, int CHW, int M, kdip_stream_t s);
 /* transpose(flatten=True): scatter into zeros                                                                :231-234 */
 int kdip_scatter(const float* src, const int32_t* idx, float* dst, int B, int CHW, int M, kdip_stream_t s);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Measurement operators and mat solvers — condition/measurements.py:86-244 (operators), condition/condition.py:317-439
+ * (inpainting_mat / gaussian_blur_mat / motion_blur_mat / super_resolution_mat), condition/utils.py:50-139
+ * (OrthoTransform), condition/diffpir_utils/utils_sisr.py:9-96, condition/dps_utils/resizer.py:8-198.
+ * Images are fp32 NCHW [B,3,S,S]; SR measurements [B,3,S/sf,S/sf].  The operator handle owns the OTF / mask / Resizer
+ * tables (built at create from HOST arrays); all per-call scratch is caller workspace (kdip_op_workspace_bytes).
+ * ------------------------------------------------------------------------------------------------------------ */
+#define KDIP_OP_INPAINTING 0
+#define KDIP_OP_GAUSSIAN_BLUR 1
+#define KDIP_OP_MOTION_BLUR 2
+#define KDIP_OP_SUPER_RESOLUTION 3
+#define KDIP_OT_NONE 0 /* condition/utils.py:50-67: identity */
+#define KDIP_OT_DCT 1  /* :89-103  scipy.fft.dctn(norm='ortho') over (C,H,W) */
+#define KDIP_OT_DWT 2  /* :107-139 pywt haar level 3, coeffs_to_array packing  */
+
+typedef struct {
+  int kind;             /* KDIP_OP_*                                                                       */
+  int S;                /* image side, power of two in [16,256]                                            */
+  int sf;               /* super_resolution scale factor (measurements.py:89), else ignored               */
+  float sigma_s;        /* measurement noise std (operator.sigma_s)                                        */
+  const float* psf;     /* HOST fp32 [ksize][ksize]: blur kernel (get_kernel(), measurements.py:158,198) or the
+                           bicubic SR kernel (measurements.py:95-97); NULL for inpainting                  */
+  int ksize;
+  const float* mask;    /* HOST fp32 [3][S][S] 0/1 (measurements.py:205-209); inpainting only              */
+  const float* rs_w;    /* HOST Resizer weights [S/sf][rs_taps] (resizer.py:104-168), super_resolution only */
+  const int32_t* rs_idx;/* HOST Resizer field of view [S/sf][rs_taps]                                      */
+  int rs_taps;
+} kdip_op_desc;
+
+typedef struct kdip_op kdip_op;
+int kdip_op_create(const kdip_op_desc* d, kdip_op** out);   /* allocates + synchronises (setup only) */
+void kdip_op_destroy(kdip_op* op);
+int kdip_op_workspace_bytes(const kdip_op* op, int B, size_t* bytes);
+/* operator.forward(data, noiseless = (noise == NULL)): y = A x + sigma_s * noise          measurements.py:103-111,139-148,
+ * 178-188,211-226.  noise has y's shape (drawn by the caller, torch.randn_like in the reference). */
+int kdip_op_forward(const kdip_op* op, const float* x, const float* noise, float* y, int B, void* ws, size_t ws_bytes,
+                    kdip_stream_t s);
+/* operator.transpose(y): blur A^T y (conj OTF), SR ifft2(conj(FB) fft2(upsample(y))), inpainting identity
+ *                                                                                       measurements.py:113-122,150-156,190-196,228-238 */
+int kdip_op_transpose(const kdip_op* op, const float* y, float* x, int B, void* ws, size_t ws_bytes, kdip_stream_t s);
+/* FB of pre_calculate (utils_sisr.py:79-96) as interleaved complex64 [S][S] (device), for operator.pre_calculated */
+int kdip_op_otf(const kdip_op* op, float* fb_full, kdip_stream_t s);
+/* closed-form mat for scalar x0 variance theta[b] (device, B floats)                   condition.py:322-323,356-357,408-410 */
+int kdip_mat_closed(const kdip_op* op, const float* y, const float* x0, const float* theta, float* mat, int B, void* ws,
+                    size_t ws_bytes, kdip_stream_t s);
+/* CG mat for a per-element variance map theta_map [B,3,S,S] in the domain of transform `ot`  condition.py:325-346,359-384,412-437.
+ * Batched on-device CG with scipy's semantics (x0 = 0, stop when ||r|| < tol*||b||, at most maxiter matvecs), per-image
+ * convergence.  iters_out: HOST int[B] or NULL.  Polls convergence, i.e. synchronises the stream (not graph-capturable).
+ * Returns KDIP_ENOTCONV (result still written, like the reference's warning) when an image hit maxiter. */
+int kdip_mat_cg(kdip_op* op, const float* y, const float* x0, const float* theta_map, int ot, float* mat, int B, float tol,
+                int maxiter, int* iters_out, void* ws, size_t ws_bytes, kdip_stream_t s);
+/* DPS (condition.py:140-148): r = y - forward(x0, noiseless); norm[b] = ||r_b||_2 (device, B floats); v = A^T r [B,3,S,S] */
+int kdip_dps_grad(const kdip_op* op, const float* y, const float* x0, float* v, float* norm, int B, void* ws,
+                  size_t ws_bytes, kdip_stream_t s);
+/* OrthoTransform: out = mul .* W^T x (inverse = 0; mul [B,3,S,S] or NULL) or out = W x (inverse = 1)   condition/utils.py:69-77 */
+int kdip_ortho(int ot, int inverse, const float* x, const float* mul, float* out, int B, int S, void* ws, size_t ws_bytes,
+               kdip_stream_t s);
+int kdip_ortho_workspace_bytes(int ot, int B, int S, size_t* bytes);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Implicit-GEMM convolution on the tcgen05 tensor cores (the UNet's conv3x3 / conv1x1 / qkv / proj and their
@@ -178,6 +249,27 @@ int kdip_unet_forward(kdip_unet* u, const float* x, const float* x_scale, const 
  * condition/condition.py:136,146,155,172,269).  seed [N,6,S,S] fp32. */
 int kdip_unet_vjp(kdip_unet* u, const float* seed, int N, float* grad_x, void* workspace, size_t ws_bytes,
                   kdip_stream_t s);
+
+/* Instrumented forward + input-VJP: the same launch lists with a CUDA-event pair around every step, summed by class.
+ * Used by bench.py for the live roofline of the dominant kernel (conv_gemm_kernel); synchronises the stream. */
+typedef struct {
+  float conv_ms;        /* device time inside tcgen05 implicit-GEMM conv launches                        */
+  float other_ms;       /* GroupNorm / attention / small-conv / embedding kernels                        */
+  float total_ms;       /* first launch to last (includes gaps)                                          */
+  double conv_flops;    /* algorithmic FLOPs of those conv launches (2 x MAC, padded channels excluded)  */
+  int conv_launches;
+  int other_steps;
+} kdip_unet_profile_t;
+int kdip_unet_profile(kdip_unet* u, const float* x, const float* x_scale, const float* t, const float* seed, int N, float* out,
+                      float* grad_x, void* workspace, size_t ws_bytes, kdip_stream_t s, kdip_unet_profile_t* prof);
+
+/* State-dict schema of UNetModel for an architecture (names / shapes of unet.py:463-618), so the host-side module can
+ * declare its parameters without restating the block walk.  shape_out: int64[4]. */
+int kdip_unet_schema_count(const kdip_unet_arch* arch, int* n);
+int kdip_unet_schema_entry(const kdip_unet_arch* arch, int index, char* name_out, int name_cap, int64_t* shape_out,
+                           int* ndim);
+/* Pre-head feature [N, C0, S, S] fp32 of the last forward (UNetModel.forward(return_feature=True), unet.py:665-666). */
+int kdip_unet_feature(kdip_unet* u, int N, float* feat, kdip_stream_t s);
 
 /* ------------------------------------------------------------------------------------------------------------
  * UNet building blocks, exported for per-layer parity tests (tests/test_layers_gpu.py).  Activations are bf16 NHWC.

@@ -1,0 +1,320 @@
+"""ConditionDenoiser — E[x0 | x_t, y] under a Gaussian posterior with optimal covariance (condition/condition.py:41-439).
+
+Same classes, constructor arguments, guidance names and mat-solver registry as the reference; batch-capable (the
+reference asserts B == 1, condition.py:84; here every image of the batch carries its own measurement y and all
+per-image scalars broadcast as [B]).  One model evaluation is:
+
+    UNet forward (libkdip, bf16 tcgen05)  ->  p_mean_variance epilogue + x0 covariance (one fused kernel)
+    ->  mat = A^T (sigma_s^2 I + A Sigma A^T)^-1 (y - A x0)   (closed form: 3-6 FFT kernels; per-pixel Sigma: on-device batched CG)
+    ->  likelihood score = J^T mat through the clamp and the UNet (hand-written input-VJP)
+    ->  hat_x0 = clip(x0 + sigma^2 * score, -1, 1)            (fused combine kernel)
+
+sigma is uniform across the batch inside a sampler call; the sigma-dependent branches (MLE threshold, scalar vs.
+per-pixel covariance) are decided on the host from the schedule value the sampler attaches to the sigma tensor, so a
+model evaluation has no device->host synchronisation except the CG convergence poll.
+
+Out of scope (not reachable from the BASELINE configurations): 'autoI' (needs gpytorch), 'stsl' / 'stsl+mle'.
+"""
+from abc import abstractmethod
+from warnings import warn  # noqa: F401  (mat solvers warn on CG non-convergence through kdip.ops)
+
+import numpy as np
+import torch
+from torch import nn
+
+from guided_diffusion.gaussian_diffusion import GaussianDiffusion, _extract_into_tensor  # noqa: F401
+from guided_diffusion.unet import UNetModel
+from k_diffusion.external import OpenAIDenoiser, OpenAIDenoiserV2
+from kdip import ops
+
+from .utils import OrthoTransform
+
+
+def _host_sigma(sigma, B):
+    """Per-image sigma as python floats.  The kdip samplers attach the host value; otherwise read it back (one sync)."""
+    h = getattr(sigma, "_kdip_host", None)
+    if h is not None:
+        return [float(h)] * B
+    v = [float(s) for s in sigma.detach().flatten().tolist()]
+    return v * B if len(v) == 1 else v
+
+
+def _uniform(sig):
+    if any(s != sig[0] for s in sig):
+        raise ValueError("kdip ConditionDenoiser: sigma must be identical across the batch (it is inside a sampler call)")
+    return sig[0]
+
+
+def _dev(vals, device):
+    return torch.tensor(vals, device=device, dtype=torch.float32)
+
+
+class ConditionDenoiser(nn.Module):
+    '''Approximate E[x0|xt, y] given variational Gaussian posterior'''
+
+    def __init__(self, operator, measurement, guidance, device='cpu', zeta=None, lambda_=None, eta=None,
+                 num_hutchinson_samples=None, mle_sigma_thres=0.2, ortho_tf_type=None):
+        super().__init__()
+        self.operator = operator
+        self.y, self.y_flatten = measurement
+        self.guidance = guidance
+        self.zeta = zeta
+        self.lambda_ = lambda_
+        self.eta = eta
+        self.num_hutchinson_samples = num_hutchinson_samples
+        self.mle_sigma_thres = mle_sigma_thres
+        self.device = device
+        self.ortho_tf_type = ortho_tf_type
+        self.ortho_tf = OrthoTransform(ortho_tf_type)
+        self.mat_solver = __MAT_SOLVER__[operator.name]
+        self._ctx = None
+
+    @abstractmethod
+    def uncond_pred(self, x, sigma):
+        raise NotImplementedError
+
+    # ---- pieces the guidance implementations share --------------------------------------------------------------
+    def _y_for(self, B):
+        y = self.y
+        if y.shape[0] != B:
+            if y.shape[0] != 1:
+                raise ValueError(f"measurement batch {y.shape[0]} does not match x batch {B}")
+            y = y.expand(B, *y.shape[1:]).contiguous()
+        return y
+
+    def _score(self, x0_mean, v):
+        """J^T v for J = d x0_mean / d x_t: clamp mask and scalings (kdip_pmv_vjp_seed) then the UNet input-VJP.
+        Returns the two terms (g wrt the scaled UNet input, direct) that kdip_guidance_combine sums."""
+        raise NotImplementedError
+
+    def _theta(self, x0_var, theta0_var):
+        return x0_var if self.ortho_tf_type is None else theta0_var
+
+    def forward(self, x, sigma):
+        B = x.shape[0]
+        sig = _uniform(_host_sigma(sigma, B))
+        g = self.guidance
+        if g in ("dps+mle", "pgdm+mle"):
+            g = "I" if sig < self.mle_sigma_thres else g.split("+")[0]
+        x = x.detach().contiguous().float()
+        if g == "uncond":
+            x0_mean = self.uncond_pred(x, sigma)[0]
+            return ops.guidance_combine(x0_mean, x0_mean, None, _dev([0.0] * B, x.device))
+        if g == "I":
+            return self._type_I_guidance_impl(x, sigma)
+        if g == "II":
+            return self._type_II_guidance_impl(x, sigma)
+        if g == "dps":
+            return self._dps_guidance_impl(x, sigma)
+        if g == "pgdm":
+            return self._pgdm_guidance_impl(x, sigma)
+        if g == "diffpir":
+            return self._diffpir_guidance_impl(x, sigma)
+        if g in ("autoI", "stsl", "stsl+mle"):
+            raise NotImplementedError(f"guidance '{self.guidance}' is outside the kdip hot path (SURVEY.md §2 #2)")
+        raise ValueError(f"Invalid guidance type: '{self.guidance}'.")
+
+    def _dps_guidance_impl(self, x, sigma):
+        """condition.py:140-148: x0 - sigma^2 zeta grad_x ||y - A(x0)||_2  (per-image norm; equals the reference at B = 1)."""
+        assert self.zeta is not None, "zeta must be specified for DPS guidance"
+        B = x.shape[0]
+        sig = _uniform(_host_sigma(sigma, B))
+        x0_mean = self.uncond_pred(x, sigma)[0]
+        v, norm = self.operator.handle.dps_grad(self._y_for(B), x0_mean)
+        g, direct = self._score(x0_mean, v)
+        coef = float(np.float32(sig) ** 2 * np.float32(self.zeta)) / norm   # [B] device scalars: sigma^2 zeta / ||r_b||
+        return ops.guidance_combine(x0_mean, g, direct, coef, self._ctx["c_in_dev"])
+
+    def _pgdm_guidance_impl(self, x, sigma):
+        """condition.py:150-157: theta = r^2 = sigma^2/(1+sigma^2); x0 + sigma^2 r^2 J^T mat."""
+        B = x.shape[0]
+        sig = np.float32(_uniform(_host_sigma(sigma, B)))
+        x0_mean = self.uncond_pred(x, sigma)[0]
+        r2 = sig ** 2 / (1 + sig ** 2)
+        x0_var = _dev([float(r2)] * B, x.device)
+        mat = self.mat_solver(self.operator, self._y_for(B), x0_mean, x0_var)
+        g, direct = self._score(x0_mean, mat)
+        return ops.guidance_combine(x0_mean, g, direct, _dev([float(sig ** 2 * r2)] * B, x.device), self._ctx["c_in_dev"])
+
+    def _diffpir_guidance_impl(self, x, sigma):
+        """condition.py:159-165: x0 + theta * mat with theta = sigma^2 / lambda (no VJP)."""
+        assert self.lambda_ is not None, "lambda_ must be specified for DiffPIR guidance"
+        B = x.shape[0]
+        sig = np.float32(_uniform(_host_sigma(sigma, B)))
+        x0_mean = self.uncond_pred(x, sigma)[0]
+        x0_var = _dev([float(sig ** 2 / np.float32(self.lambda_))] * B, x.device)
+        mat = self.mat_solver(self.operator, self._y_for(B), x0_mean, x0_var)
+        return ops.guidance_combine(x0_mean, mat, None, x0_var)
+
+    def _type_I_guidance_impl(self, x, sigma):
+        """condition.py:167-174: x0 + sigma^2 J^T mat."""
+        B = x.shape[0]
+        sig = np.float32(_uniform(_host_sigma(sigma, B)))
+        x0_mean, x0_var, theta0_var = self.uncond_pred(x, sigma)
+        mat = self.mat_solver(self.operator, self._y_for(B), x0_mean, self._theta(x0_var, theta0_var), self.ortho_tf)
+        g, direct = self._score(x0_mean, mat)
+        return ops.guidance_combine(x0_mean, g, direct, _dev([float(sig ** 2)] * B, x.device), self._ctx["c_in_dev"])
+
+    def _type_II_guidance_impl(self, x, sigma):
+        """condition.py:176-183: x0 + W(theta .* W^T mat) (no VJP)."""
+        B = x.shape[0]
+        x0_mean, x0_var, theta0_var = self.uncond_pred(x, sigma)
+        theta = self._theta(x0_var, theta0_var)
+        mat = self.mat_solver(self.operator, self._y_for(B), x0_mean, theta, self.ortho_tf)
+        if theta.dim() <= 1:                                   # scalar variance: W(theta W^T mat) = theta * mat
+            return ops.guidance_combine(x0_mean, mat, None, theta.reshape(-1).expand(B).contiguous())
+        upd = ops.ortho(self.ortho_tf_type, ops.ortho(self.ortho_tf_type, mat, mul=theta), inverse=True)
+        return ops.guidance_combine(x0_mean, upd, None, _dev([1.0] * B, x.device))
+
+
+class ConditionOpenAIDenoiser(ConditionDenoiser):
+    """condition.py:211-274 (v1: OpenAI UNet + GaussianDiffusion, integer t, clamped x0)."""
+
+    def __init__(self, inner_model, diffusion: GaussianDiffusion, x0_cov_type, recon_mse, **kwargs):
+        super().__init__(**kwargs)
+        if not isinstance(inner_model, UNetModel):
+            raise TypeError("kdip ConditionOpenAIDenoiser needs the kdip guided_diffusion.unet.UNetModel as inner_model")
+        self.inner_model = inner_model
+        self.diffusion = diffusion
+        self.denoiser = OpenAIDenoiser(inner_model, diffusion, device=self.device)
+        self.x0_cov_type = x0_cov_type
+        self.recon_mse = recon_mse
+        if recon_mse is not None:
+            for key in self.recon_mse.keys():
+                self.recon_mse[key] = self.recon_mse[key].to(self.device)
+            self._recon_sigmas_host = self.recon_mse['sigmas'].detach().float().cpu().numpy()
+
+    def uncond_pred(self, x, sigma):
+        """-> (x0_mean [B,3,H,W], x0_var, theta0_var); x0_var is [B] (per-image scalar) or a [B,3,H,W] map."""
+        B = x.shape[0]
+        sig_list = _host_sigma(sigma, B)
+        sig = np.float32(_uniform(sig_list))
+        c_in = [float(np.float32(1) / np.sqrt(sig * sig + np.float32(1)))] * B           # external.py:97-100
+        t_int = [int(self.denoiser.sigma_to_t_host(float(sig)))] * B                     # condition.py:233: .long() truncates
+        tm = getattr(self.diffusion, "timestep_map", None)
+        t_model = [tm[t] for t in t_int] if tm is not None else t_int                    # respace.py:123-128
+        c_in_dev = _dev(c_in, x.device)
+        eng = self.inner_model.engine()
+        out = eng.forward(x, _dev([float(t) for t in t_model], x.device), x_scale=c_in_dev)
+        ct = self.x0_cov_type
+        mle = bool(sig < self.mle_sigma_thres)
+        sc = ops.pmv_scalars(self.diffusion, t_int, c_in, x.device)
+        x0_mean, var = ops.pmv_epilogue(out, x, sc, want_var=(ct == 'convert' and mle))
+        self._ctx = dict(sc=sc, c_in_dev=c_in_dev, eng=eng, token=eng.forward_token)
+        r2 = _dev([float(sig ** 2 / (1 + sig ** 2))] * B, x.device)
+        if ct == 'convert':
+            x0_var = var if mle else r2                                                   # Eq. (22), fused in the epilogue
+        elif ct == 'analytic':
+            assert self.recon_mse is not None
+            if mle:
+                idx = int(np.abs(self._recon_sigmas_host - sig).argmin())
+                x0_var = self.recon_mse['mse_list'][idx].reshape(1).float().expand(B).contiguous()
+            else:
+                x0_var = r2
+        elif ct == 'pgdm':
+            x0_var = r2
+        elif ct == 'dps':
+            x0_var = torch.zeros(B, device=x.device)
+        elif ct == 'diffpir':
+            assert self.lambda_ is not None
+            x0_var = _dev([float(sig ** 2 / np.float32(self.lambda_))] * B, x.device)
+        elif ct == 'tmpd':
+            # sigma^2 * grad_x sum(x0_mean): one extra input-VJP seeded with ones (condition.py:268-269)
+            g, direct = self._score(x0_mean, torch.ones_like(x0_mean))
+            x0_var = ops.lincomb(g, direct, _dev([float(sig ** 2) * c for c in c_in], x.device), _dev([float(sig ** 2)] * B, x.device))
+        else:
+            raise ValueError('Invalid posterior covariance type.')
+        return x0_mean, x0_var, x0_var
+
+    def _score(self, x0_mean, v):
+        c = self._ctx
+        if c["eng"].forward_token != c["token"]:
+            raise RuntimeError("the UNet engine ran another forward since uncond_pred; its saved activations are gone")
+        seed, direct = ops.pmv_vjp_seed(x0_mean, v, c["sc"])
+        return c["eng"].vjp(seed), direct
+
+
+class ConditionOpenAIDenoiserV2(ConditionDenoiser):
+    """condition.py:277-300 (v2: DWT-Var head, continuous t, no clamp)."""
+
+    def __init__(self, denoiser: OpenAIDenoiserV2, **kwargs):
+        super().__init__(**kwargs)
+        self.denoiser = denoiser
+        ortho_tf_type = kwargs.get('ortho_tf_type', None)
+        if ortho_tf_type is not None:
+            assert ortho_tf_type == denoiser.ortho_tf_type, "ortho_tf_type must match the one used in the denoiser"
+
+    def uncond_pred(self, x, sigma):
+        B = x.shape[0]
+        sig_list = _host_sigma(sigma, B)
+        sig = np.float32(_uniform(sig_list))
+        out, cov = self.denoiser.raw(x, sig_list)
+        mle = bool(sig < self.mle_sigma_thres)
+        x0_mean, x0_var, theta0_var = ops.v2_epilogue(out, cov, x, _dev(sig_list, x.device), want_var=mle)
+        if not mle:
+            x0_var = theta0_var = _dev([float(sig ** 2 / (1 + sig ** 2))] * B, x.device)
+        self._ctx = None
+        return x0_mean, x0_var, theta0_var
+
+    def _score(self, x0_mean, v):
+        raise NotImplementedError("the v2 (DWT-Var) denoiser is used with VJP-free guidance (type II / DiffPIR) on this path")
+
+
+# ---------------------------------------------
+# Implementation of mat solver (computing v)
+# ---------------------------------------------
+
+__MAT_SOLVER__ = {}
+
+
+def register_mat_solver(name):
+    def wrapper(func):
+        __MAT_SOLVER__[name] = func
+        return func
+    return wrapper
+
+
+def _solve(operator, y, x0_mean, theta0_var, ortho_tf):
+    """Scalar variance ([B] / 0-dim / [1]) -> closed form; per-element map -> batched device CG (tol 1e-4, <= 1000 its)."""
+    B = x0_mean.shape[0]
+    if theta0_var.dim() <= 1:
+        theta = theta0_var.reshape(-1).float()
+        if theta.numel() == 1 and B > 1:
+            theta = theta.expand(B)
+        return operator.handle.mat_closed(y, x0_mean, theta.contiguous())
+    theta = theta0_var
+    if theta.shape[0] != B:
+        theta = theta.expand(B, *theta.shape[1:])
+    return operator.handle.mat_cg(y, x0_mean, theta, ot=ortho_tf.ortho_tf_type, tol=1e-4, maxiter=1000)
+
+
+@register_mat_solver('inpainting')
+@torch.no_grad()
+def inpainting_mat(operator, y, x0_mean, theta0_var, ortho_tf=OrthoTransform()):
+    """condition.py:317-348."""
+    return _solve(operator, y, x0_mean, theta0_var, ortho_tf)
+
+
+@torch.no_grad()
+def _deblur_mat(operator, y, x0_mean, theta0_var, ortho_tf=OrthoTransform()):
+    """condition.py:351-386."""
+    return _solve(operator, y, x0_mean, theta0_var, ortho_tf)
+
+
+@register_mat_solver('gaussian_blur')
+@torch.no_grad()
+def gaussian_blur_mat(operator, y, x0_mean, theta0_var, ortho_tf=OrthoTransform()):
+    return _deblur_mat(operator, y, x0_mean, theta0_var, ortho_tf)
+
+
+@register_mat_solver('motion_blur')
+@torch.no_grad()
+def motion_blur_mat(operator, y, x0_mean, theta0_var, ortho_tf=OrthoTransform()):
+    return _deblur_mat(operator, y, x0_mean, theta0_var, ortho_tf)
+
+
+@register_mat_solver('super_resolution')
+@torch.no_grad()
+def super_resolution_mat(operator, y, x0_mean, theta0_var, ortho_tf=OrthoTransform()):
+    """condition.py:401-439."""
+    return _solve(operator, y, x0_mean, theta0_var, ortho_tf)

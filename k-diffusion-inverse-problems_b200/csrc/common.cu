@@ -2,6 +2,8 @@
 #include <cudaTypedefs.h>
 #include <stdarg.h>
 
+#include <atomic>
+
 #include "kdip_common.cuh"
 
 namespace kdip {
@@ -19,6 +21,9 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
   set_error("CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
   return KDIP_ECUDA;
 }
+
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 int num_sms() {
   static int sms = 0;
@@ -79,6 +84,7 @@ int encode_tmap_bf16_2d(CUtensorMap* m, const void* base, uint64_t cols, uint64_
 
 extern "C" const char* kdip_last_error(void) { return kdip::g_err; }
 extern "C" int kdip_version(void) { return 1; }
+extern "C" unsigned long long kdip_launch_count(void) { return kdip::g_launches.load(std::memory_order_relaxed); }
 
 extern "C" int kdip_device_check(int* sm_count) {
   int dev = 0;

@@ -80,10 +80,10 @@ __global__ void pmv_kernel(const float* __restrict__ out, const float* __restric
       float4 v = ld4(ob + 3 * HW * 4, i), o;
       // variance = exp(frac*max_log + (1-frac)*min_log), frac = (v+1)/2 ; Convert: clip((variance - beta~)/coef1^2, 1e-6)
       float f;
-      f = (v.x + 1.f) * 0.5f; o.x = fmaxf((expf(f * s.max_log + (1.f - f) * s.min_log) - s.post_var) * s.inv_coef1_sq, 1e-6f);
-      f = (v.y + 1.f) * 0.5f; o.y = fmaxf((expf(f * s.max_log + (1.f - f) * s.min_log) - s.post_var) * s.inv_coef1_sq, 1e-6f);
-      f = (v.z + 1.f) * 0.5f; o.z = fmaxf((expf(f * s.max_log + (1.f - f) * s.min_log) - s.post_var) * s.inv_coef1_sq, 1e-6f);
-      f = (v.w + 1.f) * 0.5f; o.w = fmaxf((expf(f * s.max_log + (1.f - f) * s.min_log) - s.post_var) * s.inv_coef1_sq, 1e-6f);
+      f = (v.x + 1.f) * 0.5f; o.x = fmaxf((expf(f * s.max_log + (1.f - f) * s.min_log) - s.post_var) / s.coef1_sq, 1e-6f);
+      f = (v.y + 1.f) * 0.5f; o.y = fmaxf((expf(f * s.max_log + (1.f - f) * s.min_log) - s.post_var) / s.coef1_sq, 1e-6f);
+      f = (v.z + 1.f) * 0.5f; o.z = fmaxf((expf(f * s.max_log + (1.f - f) * s.min_log) - s.post_var) / s.coef1_sq, 1e-6f);
+      f = (v.w + 1.f) * 0.5f; o.w = fmaxf((expf(f * s.max_log + (1.f - f) * s.min_log) - s.post_var) / s.coef1_sq, 1e-6f);
       st4(var + (size_t)b * 3 * HW * 4, i, o);
     }
   }
@@ -125,6 +125,45 @@ __global__ void combine_kernel(const float* __restrict__ x0, const float* __rest
     o.z = fminf(fmaxf(m.z + k * (ci * u.z + d.z), -1.f), 1.f);
     o.w = fminf(fmaxf(m.w + k * (ci * u.w + d.w), -1.f), 1.f);
     st4(hat, off + i, o);
+  }
+}
+
+// out = a[b]*x + c[b]*y (y may be NULL); no clipping (TMPD's Jacobian-diagonal proxy, condition.py:268-269)
+__global__ void lincomb_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ a,
+                               const float* __restrict__ c, float* __restrict__ out, int CHW4) {
+  const int b = blockIdx.y;
+  const float ka = a[b], kc = c ? c[b] : 0.f;
+  const size_t off = (size_t)b * CHW4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)CHW4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 u = ld4(x, off + i), o;
+    float4 v = y ? ld4(y, off + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    o.x = ka * u.x + kc * v.x; o.y = ka * u.y + kc * v.y; o.z = ka * u.z + kc * v.z; o.w = ka * u.w + kc * v.w;
+    st4(out, off + i, o);
+  }
+}
+
+// v2 (DWT-Var) epilogue: x0 = eps*c_out + x, c_out = -sigma; variances exp(logvar)*c_out^2   (condition.py:287-300)
+__global__ void v2_epilogue_kernel(const float* __restrict__ out6, const float* __restrict__ cov6, const float* __restrict__ x,
+                                   const float* __restrict__ sigma, float* __restrict__ x0, float* __restrict__ var,
+                                   float* __restrict__ var_ot, int HW4) {
+  const int b = blockIdx.y;
+  const float c_out = -sigma[b];
+  const float c2 = c_out * c_out;
+  const size_t HW = (size_t)HW4;
+  const float* ob = out6 + (size_t)b * 6 * HW * 4;
+  const float* cb = cov6 + (size_t)b * 6 * HW * 4;
+  const size_t o3 = (size_t)b * 3 * HW * 4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < 3 * HW; i += (size_t)gridDim.x * blockDim.x) {
+    float4 e = ld4(ob, i), xv = ld4(x + o3, i), r;
+    r.x = e.x * c_out + xv.x; r.y = e.y * c_out + xv.y; r.z = e.z * c_out + xv.z; r.w = e.w * c_out + xv.w;
+    st4(x0 + o3, i, r);
+    if (var) {
+      float4 l = ld4(cb, i), lo = ld4(cb + 3 * HW * 4, i), v, vo;
+      v.x = expf(l.x) * c2; v.y = expf(l.y) * c2; v.z = expf(l.z) * c2; v.w = expf(l.w) * c2;
+      vo.x = expf(lo.x) * c2; vo.y = expf(lo.y) * c2; vo.z = expf(lo.z) * c2; vo.w = expf(lo.w) * c2;
+      st4(var + o3, i, v);
+      st4(var_ot + o3, i, vo);
+    }
   }
 }
 
@@ -233,6 +272,28 @@ extern "C" int kdip_guidance_combine(const float* x0_mean, const float* unet_gra
   REQ_ALIGN16(x0_mean); REQ_ALIGN16(unet_grad); REQ_ALIGN16(direct); REQ_ALIGN16(hat_x0); REQ_MULT4(CHW);
   KDIP_REQUIRE(B > 0, KDIP_ESHAPE, "guidance_combine: B must be > 0");
   combine_kernel<<<grid_by(CHW / 4, B), EW_THREADS, 0, (cudaStream_t)s>>>(x0_mean, unet_grad, direct, coef, c_in, hat_x0, CHW / 4);
+  KDIP_LAUNCH_CHECK();
+  return KDIP_OK;
+}
+
+extern "C" int kdip_lincomb(const float* x, const float* y, const float* a, const float* c, float* out, int B, int CHW,
+                            kdip_stream_t s) {
+  REQ_ALIGN16(x); REQ_ALIGN16(y); REQ_ALIGN16(out); REQ_MULT4(CHW);
+  KDIP_REQUIRE(B > 0 && a != nullptr && (y == nullptr || c != nullptr), KDIP_EINVAL, "lincomb: bad argument");
+  lincomb_kernel<<<grid_by(CHW / 4, B), EW_THREADS, 0, (cudaStream_t)s>>>(x, y, a, c, out, CHW / 4);
+  KDIP_LAUNCH_CHECK();
+  return KDIP_OK;
+}
+
+extern "C" int kdip_v2_epilogue(const float* unet_out, const float* cov_out, const float* x, const float* sigma, float* x0_mean,
+                                float* x0_var, float* theta0_var, int B, int HW, kdip_stream_t s) {
+  REQ_ALIGN16(unet_out); REQ_ALIGN16(cov_out); REQ_ALIGN16(x); REQ_ALIGN16(x0_mean); REQ_ALIGN16(x0_var); REQ_ALIGN16(theta0_var);
+  REQ_MULT4(HW);
+  KDIP_REQUIRE(B > 0 && sigma != nullptr, KDIP_EINVAL, "v2_epilogue: bad argument");
+  KDIP_REQUIRE((x0_var == nullptr) == (theta0_var == nullptr), KDIP_EINVAL, "v2_epilogue: x0_var and theta0_var go together");
+  KDIP_REQUIRE(x0_var == nullptr || cov_out != nullptr, KDIP_EINVAL, "v2_epilogue: variances need cov_out");
+  v2_epilogue_kernel<<<grid_by(3 * HW / 4, B), EW_THREADS, 0, (cudaStream_t)s>>>(unet_out, cov_out, x, sigma, x0_mean, x0_var,
+                                                                                   theta0_var, HW / 4);
   KDIP_LAUNCH_CHECK();
   return KDIP_OK;
 }

@@ -54,10 +54,9 @@ __device__ __forceinline__ void fft_smem(float2* buf, int ld, int T, int S, int 
 
 // ---------------------------------------------------------------------------------------------------------------------
 // rows, real -> half spectrum.  grid = P * S / (2T) blocks; block b handles rows [b*2T, b*2T + 2T) of the flattened [P*S] rows
-// optional prologue: in = x * premul (elementwise map of the same shape), or in = x - sub
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(FFT_THREADS) rows_r2c_kernel(const float* __restrict__ x, const float* __restrict__ premul,
-                                                               float2* __restrict__ out, int S, int logS, int T) {
+__global__ void __launch_bounds__(FFT_THREADS) rows_r2c_kernel(const float* __restrict__ x, float2* __restrict__ out, int S, int logS,
+                                                               int T) {
   extern __shared__ float2 sm[];
   float2* tw = sm;               // [S/2]
   float2* buf = sm + S / 2;      // [T][S+1]
@@ -67,8 +66,7 @@ __global__ void __launch_bounds__(FFT_THREADS) rows_r2c_kernel(const float* __re
   const size_t row0 = (size_t)blockIdx.x * 2 * T;
   for (int i = threadIdx.x; i < 2 * T * S; i += blockDim.x) {
     const int r = i / S, c = i - r * S;
-    float v = x[(row0 + r) * S + c];
-    if (premul) v *= premul[(row0 + r) * S + c];
+    const float v = x[(row0 + r) * S + c];
     float* dst = reinterpret_cast<float*>(&buf[(r >> 1) * ld + bitrev(c, logS)]);
     dst[r & 1] = v;
   }
@@ -124,7 +122,7 @@ __global__ void __launch_bounds__(FFT_THREADS) rows_c2r_kernel(const float2* __r
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// columns: forward FFT along y, pointwise spectral op, inverse FFT along y (either side optional)
+// columns: forward FFT along y, then (unless SPEC_FORWARD_ONLY) a pointwise spectral op and the inverse FFT along y
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(FFT_THREADS) cols_kernel(const float2* __restrict__ in, float2* __restrict__ out, int S, int logS,
                                                            SpecOp op) {
@@ -139,7 +137,6 @@ __global__ void __launch_bounds__(FFT_THREADS) cols_kernel(const float2* __restr
   const int p = blockIdx.x / groups;               // plane
   const int kx0 = (blockIdx.x - p * groups) * CW;
   make_twiddles(tw, S);
-  const bool fwd = op.mode != SPEC_INVERSE_ONLY;
   const bool inv = op.mode != SPEC_FORWARD_ONLY;
   const float2* src = in + (size_t)p * S * Sh;
   for (int i = threadIdx.x; i < S * CW; i += blockDim.x) {
@@ -147,11 +144,9 @@ __global__ void __launch_bounds__(FFT_THREADS) cols_kernel(const float2* __restr
     const int kx = kx0 + c;
     float2 v = make_float2(0.f, 0.f);
     if (kx < Sh) v = src[(size_t)ky * Sh + kx];
-    if (fwd) bufA[c * ld + bitrev(ky, logS)] = v;
-    else bufA[c * ld + ky] = v;
+    bufA[c * ld + bitrev(ky, logS)] = v;
   }
-  if (fwd) fft_smem(bufA, ld, CW, S, logS, tw, false);
-  else __syncthreads();
+  fft_smem(bufA, ld, CW, S, logS, tw, false);
   // pointwise op in natural order
   float2* res = bufA;
   if (inv) {
@@ -166,20 +161,15 @@ __global__ void __launch_bounds__(FFT_THREADS) cols_kernel(const float2* __restr
           float2 m = op.otf[sidx];
           if (op.conj_otf) m.y = -m.y;
           v = cmul(v, m);
-        } else if (op.mode == SPEC_BLUR_CLOSED) {
-          // V = (Fy - FB*X) * conj(FB) / (sigma_s^2 + theta*|FB|^2)          condition/condition.py:357
+        } else if (op.mode == SPEC_DIV_CONJ) {
+          // fft2(r) / (sigma_s^2 + theta*|FB|^2) * conj(FB)                         condition/condition.py:357
           const float2 fb = op.otf[sidx];
-          const float2 fy = op.fy[(size_t)p * S * Sh + sidx];
-          const float2 ax = cmul(fb, v);
-          const float2 r = make_float2(fy.x - ax.x, fy.y - ax.y);
           const float den = op.sigma_s2 + op.theta[img] * (fb.x * fb.x + fb.y * fb.y);
-          const float2 q = make_float2(r.x / den, r.y / den);
-          v = cmul(q, cconj(fb));
-        } else if (op.mode == SPEC_RESIDUAL) {
-          // R = Fy - FB*X  (spectrum of y - A x; used by DPS and as the CG right-hand side)
-          const float2 ax = cmul(op.otf[sidx], v);
-          const float2 fy = op.fy[(size_t)p * S * Sh + sidx];
-          v = make_float2(fy.x - ax.x, fy.y - ax.y);
+          v = cmul(make_float2(v.x / den, v.y / den), cconj(fb));
+        } else if (op.mode == SPEC_DIV_TABLE) {
+          // fft2(r) / (sigma_s^2 + theta*invW)                                       condition/condition.py:409-410
+          const float den = op.sigma_s2 + op.theta[img] * op.table[sidx];
+          v = make_float2(v.x / den, v.y / den);
         }
       }
       bufB[c * ld + bitrev(ky, logS)] = v;
@@ -216,12 +206,12 @@ int check_fft_size(int S, int planes) {
   return KDIP_OK;
 }
 
-int launch_rows_r2c(const float* x, const float* premul, float2* out, int planes, int S, cudaStream_t s) {
+int launch_rows_r2c(const float* x, float2* out, int planes, int S, cudaStream_t s) {
   int rc = check_fft_size(S, planes);
   if (rc) return rc;
   const int T = rows_T(S, planes);
   const size_t smem = (size_t)(S / 2 + T * (S + 1)) * sizeof(float2);
-  rows_r2c_kernel<<<(unsigned)((size_t)planes * S / (2 * T)), FFT_THREADS, smem, s>>>(x, premul, out, S, ilog2(S), T);
+  rows_r2c_kernel<<<(unsigned)((size_t)planes * S / (2 * T)), FFT_THREADS, smem, s>>>(x, out, S, ilog2(S), T);
   KDIP_LAUNCH_CHECK();
   return KDIP_OK;
 }

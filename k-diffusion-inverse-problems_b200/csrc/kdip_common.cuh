@@ -21,7 +21,12 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
     cudaError_t _e = (expr);                                                            \
     if (_e != cudaSuccess) return ::kdip::cuda_fail(_e, #expr, __FILE__, __LINE__);     \
   } while (0)
-#define KDIP_LAUNCH_CHECK() KDIP_CUDA(cudaGetLastError())
+// every kernel launch in the library is followed by this: it also feeds kdip_launch_count() (bench.py's gpu_launches)
+#define KDIP_LAUNCH_CHECK()              \
+  do {                                   \
+    ::kdip::count_launch();              \
+    KDIP_CUDA(cudaGetLastError());       \
+  } while (0)
 #define KDIP_REQUIRE(cond, code, ...)                                                   \
   do {                                                                                  \
     if (!(cond)) {                                                                      \
@@ -31,6 +36,7 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
   } while (0)
 
 int num_sms();
+void count_launch();
 
 // ---- small device helpers ----------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

@@ -67,7 +67,21 @@ struct Act {
   int H, W, C;
 };
 
-typedef std::function<int(cudaStream_t)> Op;
+// one step of a launch list; conv steps carry their algorithmic FLOPs for kdip_unet_profile
+struct Op {
+  std::function<int(cudaStream_t)> fn;
+  bool is_conv = false;
+  double flops = 0.0;
+  template <class F>
+  Op(F f) : fn(f) {}
+  int operator()(cudaStream_t s) const { return fn(s); }
+};
+
+static double conv_flops(const kdip_conv_desc& d) {
+  double k = 0;
+  for (int i = 0; i < d.nseg; ++i) k += (double)d.seg[i].C * d.seg[i].taps;
+  return 2.0 * d.N * d.H * d.W * (double)d.Cout * k;
+}
 
 }  // namespace kdip
 
@@ -477,15 +491,22 @@ static int build_launch_plan(kdip_unet* u, int N, void* ws, size_t ws_bytes, siz
   bf16* g3 = (bf16*)B.alloc(scratch_bytes);
   bf16* g4 = (bf16*)B.alloc(scratch_bytes);
 
+  double last_conv_flops = 0.0;
   auto conv = [&](const kdip_conv_desc& d) -> ConvPlan* {
     if (!emit) return nullptr;
     int r;
     ConvPlan* p = make_conv(u, d, &r);
     if (r != KDIP_OK && rc == KDIP_OK) rc = r;
+    last_conv_flops = conv_flops(d);
     return p;
   };
   auto add_conv_op = [&](std::vector<Op>& ops, ConvPlan* p) {
-    if (emit && p) ops.push_back([p](cudaStream_t s) { return conv_plan_launch(p, s); });
+    if (emit && p) {
+      Op o([p](cudaStream_t s) { return conv_plan_launch(p, s); });
+      o.is_conv = true;
+      o.flops = last_conv_flops;
+      ops.push_back(o);
+    }
   };
   auto stats_op = [&](std::vector<Op>& ops, const Act& t) {
     if (!emit) return;
@@ -783,6 +804,75 @@ static int build_launch_plan(kdip_unet* u, int N, void* ws, size_t ws_bytes, siz
   return KDIP_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// state_dict schema (names and shapes of UNetModel's parameters, unet.py:463-618) derived from the same block plan
+// ---------------------------------------------------------------------------------------------------------------------
+namespace kdip {
+struct SchemaEntry { std::string name; int64_t shape[4]; int ndim; };
+static void build_schema(const kdip_unet_arch& a, std::vector<SchemaEntry>& out) {
+  std::vector<BlockDesc> plan;
+  build_block_plan(a, plan);
+  auto add = [&](const std::string& n, std::initializer_list<int64_t> shp) {
+    SchemaEntry e;
+    e.name = n; e.ndim = (int)shp.size();
+    int i = 0;
+    for (int64_t v : shp) e.shape[i++] = v;
+    for (; i < 4; ++i) e.shape[i] = 1;
+    out.push_back(e);
+  };
+  const int64_t mc = a.model_channels, ted = 4 * mc;
+  add("time_embed.0.weight", {ted, mc}); add("time_embed.0.bias", {ted});
+  add("time_embed.2.weight", {ted, ted}); add("time_embed.2.bias", {ted});
+  for (auto& b : plan) {
+    const std::string& p = b.prefix;
+    const int64_t ci = b.cin, co = b.cout;
+    if (b.kind == 0) {
+      add(p + ".weight", {co, ci, 3, 3}); add(p + ".bias", {co});
+    } else if (b.kind == 1) {
+      add(p + ".in_layers.0.weight", {ci}); add(p + ".in_layers.0.bias", {ci});
+      add(p + ".in_layers.2.weight", {co, ci, 3, 3}); add(p + ".in_layers.2.bias", {co});
+      add(p + ".emb_layers.1.weight", {2 * co, ted}); add(p + ".emb_layers.1.bias", {2 * co});
+      add(p + ".out_layers.0.weight", {co}); add(p + ".out_layers.0.bias", {co});
+      add(p + ".out_layers.3.weight", {co, co, 3, 3}); add(p + ".out_layers.3.bias", {co});
+      if (ci != co) { add(p + ".skip_connection.weight", {co, ci, 1, 1}); add(p + ".skip_connection.bias", {co}); }
+    } else {
+      add(p + ".norm.weight", {ci}); add(p + ".norm.bias", {ci});
+      add(p + ".qkv.weight", {3 * ci, ci, 1}); add(p + ".qkv.bias", {3 * ci});
+      add(p + ".proj_out.weight", {ci, ci, 1}); add(p + ".proj_out.bias", {ci});
+    }
+  }
+  const int64_t c0 = (int64_t)(a.channel_mult[0] * mc);
+  add("out.0.weight", {c0}); add("out.0.bias", {c0});
+  add("out.2.weight", {a.out_channels, c0, 3, 3}); add("out.2.bias", {a.out_channels});
+}
+}  // namespace kdip
+
+extern "C" int kdip_unet_schema_count(const kdip_unet_arch* arch, int* n) {
+  KDIP_REQUIRE(arch && n, KDIP_EINVAL, "unet_schema_count: null argument");
+  std::vector<SchemaEntry> sc;
+  build_schema(*arch, sc);
+  *n = (int)sc.size();
+  return KDIP_OK;
+}
+extern "C" int kdip_unet_schema_entry(const kdip_unet_arch* arch, int index, char* name_out, int name_cap, int64_t* shape_out,
+                                      int* ndim) {
+  KDIP_REQUIRE(arch && name_out && shape_out && ndim && name_cap > 0, KDIP_EINVAL, "unet_schema_entry: null argument");
+  std::vector<SchemaEntry> sc;
+  build_schema(*arch, sc);
+  KDIP_REQUIRE(index >= 0 && index < (int)sc.size(), KDIP_EINVAL, "unet_schema_entry: index %d out of range", index);
+  snprintf(name_out, (size_t)name_cap, "%s", sc[index].name.c_str());
+  for (int i = 0; i < 4; ++i) shape_out[i] = sc[index].shape[i];
+  *ndim = sc[index].ndim;
+  return KDIP_OK;
+}
+
+// pre-head feature of the last forward as fp32 NCHW [N, C0, S, S] (UNetModel.forward(return_feature=True), unet.py:665-666)
+extern "C" int kdip_unet_feature(kdip_unet* u, int N, float* feat, kdip_stream_t s) {
+  KDIP_REQUIRE(u && feat && u->planned_N == N && u->hlast_ptr, KDIP_EINVAL, "unet_feature: must follow kdip_unet_forward with the same N");
+  const int S = u->arch.image_size, c0 = (int)(u->arch.channel_mult[0] * u->arch.model_channels);
+  return kdip_nhwc_bf16_to_nchw_f32(u->hlast_ptr, N, c0, S, S, feat, s);
+}
+
 extern "C" int kdip_unet_workspace_bytes(kdip_unet* u, int N, size_t* bytes) {
   KDIP_REQUIRE(u && bytes && N > 0, KDIP_EINVAL, "unet_workspace_bytes: bad argument");
   return build_launch_plan(u, N, nullptr, 0, bytes);
@@ -797,20 +887,22 @@ static int ensure_plan(kdip_unet* u, int N, void* ws, size_t ws_bytes) {
   return build_launch_plan(u, N, ws, ws_bytes, &need);
 }
 
-extern "C" int kdip_unet_forward(kdip_unet* u, const float* x, const float* x_scale, const float* t, int N, float* out,
-                                 float* cov_out, void* workspace, size_t ws_bytes, kdip_stream_t stream) {
-  KDIP_REQUIRE(u && x && t && out && N > 0, KDIP_EINVAL, "unet_forward: bad argument");
-  KDIP_REQUIRE(cov_out == nullptr || u->has_cov, KDIP_EINVAL, "unet_forward: cov_out requested but no out_cov weights were given");
-  int rc = ensure_plan(u, N, workspace, ws_bytes);
-  if (rc != KDIP_OK) return rc;
-  cudaStream_t s = (cudaStream_t)stream;
-  u->io_x = x; u->io_xscale = x_scale; u->io_t = t; u->io_out = out; u->io_cov = cov_out;
-  for (auto& op : u->fwd_ops) {
-    rc = op(s);
-    if (rc != KDIP_OK) return rc;
-  }
-  // head conv(s) into the caller's buffers
+// drop a cached per-pointer plan that is about to be replaced
+static void retire_plan(kdip_unet* u, ConvPlan* old) {
+  if (!old) return;
+  for (size_t i = 0; i < u->conv_plans.size(); ++i)
+    if (u->conv_plans[i] == old) {
+      u->conv_plans.erase(u->conv_plans.begin() + i);
+      break;
+    }
+  conv_plan_free(old);
+}
+
+// head conv(s) into the caller's buffers (plans cached per output pointer)
+static int forward_tail(kdip_unet* u, int N, float* out, float* cov_out, cudaStream_t s, double* flops) {
+  int rc;
   const int S = u->arch.image_size, c0 = (int)(u->arch.channel_mult[0] * u->arch.model_channels);
+  if (flops) *flops = 2.0 * N * S * S * 6.0 * c0 * 9;
   if (u->head_plan == nullptr || u->head_out != out) {
     kdip_conv_desc d;
     memset(&d, 0, sizeof(d));
@@ -819,6 +911,7 @@ extern "C" int kdip_unet_forward(kdip_unet* u, const float* x, const float* x_sc
     d.bias = u->b_head; d.out = out; d.out_mode = 1; d.out_scale = 1.f;
     ConvPlan* p = make_conv(u, d, &rc);
     if (rc != KDIP_OK) return rc;
+    retire_plan(u, u->head_plan);
     u->head_plan = p; u->head_out = out;
   }
   rc = conv_plan_launch(u->head_plan, s);
@@ -832,12 +925,47 @@ extern "C" int kdip_unet_forward(kdip_unet* u, const float* x, const float* x_sc
       d.bias = u->b_cov; d.out = cov_out; d.out_mode = 1; d.out_scale = 1.f;
       ConvPlan* p = make_conv(u, d, &rc);
       if (rc != KDIP_OK) return rc;
+      retire_plan(u, u->cov_plan);
       u->cov_plan = p; u->cov_out_ptr = cov_out;
     }
     rc = conv_plan_launch(u->cov_plan, s);
     if (rc != KDIP_OK) return rc;
   }
   return KDIP_OK;
+}
+
+extern "C" int kdip_unet_forward(kdip_unet* u, const float* x, const float* x_scale, const float* t, int N, float* out,
+                                 float* cov_out, void* workspace, size_t ws_bytes, kdip_stream_t stream) {
+  KDIP_REQUIRE(u && x && t && out && N > 0, KDIP_EINVAL, "unet_forward: bad argument");
+  KDIP_REQUIRE(cov_out == nullptr || u->has_cov, KDIP_EINVAL, "unet_forward: cov_out requested but no out_cov weights were given");
+  int rc = ensure_plan(u, N, workspace, ws_bytes);
+  if (rc != KDIP_OK) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  u->io_x = x; u->io_xscale = x_scale; u->io_t = t; u->io_out = out; u->io_cov = cov_out;
+  for (auto& op : u->fwd_ops) {
+    rc = op(s);
+    if (rc != KDIP_OK) return rc;
+  }
+  return forward_tail(u, N, out, cov_out, s, nullptr);
+}
+
+// conv_in input-gradient into the caller's buffer
+static int vjp_tail(kdip_unet* u, int N, float* grad_x, cudaStream_t s, double* flops) {
+  int rc;
+  const int S = u->arch.image_size, c0 = (int)(u->arch.channel_mult[0] * u->arch.model_channels);
+  if (flops) *flops = 2.0 * N * S * S * 3.0 * c0 * 9;
+  if (u->ind_plan == nullptr || u->ind_out != grad_x) {
+    kdip_conv_desc d;
+    memset(&d, 0, sizeof(d));
+    d.N = N; d.H = S; d.W = S; d.Cout_pad = 16; d.Cout = 3; d.nseg = 1;
+    d.seg[0].act = u->gin_final; d.seg[0].C = c0; d.seg[0].wgt = u->w_ind; d.seg[0].taps = 9;
+    d.out = grad_x; d.out_mode = 1; d.out_scale = 1.f;
+    ConvPlan* p = make_conv(u, d, &rc);
+    if (rc != KDIP_OK) return rc;
+    retire_plan(u, u->ind_plan);
+    u->ind_plan = p; u->ind_out = grad_x;
+  }
+  return conv_plan_launch(u->ind_plan, s);
 }
 
 extern "C" int kdip_unet_vjp(kdip_unet* u, const float* seed, int N, float* grad_x, void* workspace, size_t ws_bytes,
@@ -852,16 +980,55 @@ extern "C" int kdip_unet_vjp(kdip_unet* u, const float* seed, int N, float* grad
     rc = op(s);
     if (rc != KDIP_OK) return rc;
   }
-  const int S = u->arch.image_size, c0 = (int)(u->arch.channel_mult[0] * u->arch.model_channels);
-  if (u->ind_plan == nullptr || u->ind_out != grad_x) {
-    kdip_conv_desc d;
-    memset(&d, 0, sizeof(d));
-    d.N = N; d.H = S; d.W = S; d.Cout_pad = 16; d.Cout = 3; d.nseg = 1;
-    d.seg[0].act = u->gin_final; d.seg[0].C = c0; d.seg[0].wgt = u->w_ind; d.seg[0].taps = 9;
-    d.out = grad_x; d.out_mode = 1; d.out_scale = 1.f;
-    ConvPlan* p = make_conv(u, d, &rc);
+  return vjp_tail(u, N, grad_x, s, nullptr);
+}
+
+extern "C" int kdip_unet_profile(kdip_unet* u, const float* x, const float* x_scale, const float* t, const float* seed, int N,
+                                 float* out, float* grad_x, void* workspace, size_t ws_bytes, kdip_stream_t stream,
+                                 kdip_unet_profile_t* prof) {
+  KDIP_REQUIRE(u && x && t && out && seed && grad_x && prof && N > 0, KDIP_EINVAL, "unet_profile: bad argument");
+  int rc = ensure_plan(u, N, workspace, ws_bytes);
+  if (rc != KDIP_OK) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  u->io_x = x; u->io_xscale = x_scale; u->io_t = t; u->io_out = out; u->io_cov = nullptr;
+  u->io_seed = seed; u->io_grad = grad_x;
+  struct Rec { cudaEvent_t a, b; bool conv; double flops; };
+  std::vector<Rec> recs;
+  auto timed = [&](bool is_conv, double flops, const std::function<int()>& fn) -> int {
+    Rec r;
+    r.conv = is_conv; r.flops = flops;
+    KDIP_CUDA(cudaEventCreate(&r.a));
+    KDIP_CUDA(cudaEventCreate(&r.b));
+    KDIP_CUDA(cudaEventRecord(r.a, s));
+    int q = fn();
+    KDIP_CUDA(cudaEventRecord(r.b, s));
+    recs.push_back(r);
+    return q;
+  };
+  double fl = 0.0;
+  for (auto& op : u->fwd_ops) {
+    rc = timed(op.is_conv, op.flops, [&]() { return op(s); });
     if (rc != KDIP_OK) return rc;
-    u->ind_plan = p; u->ind_out = grad_x;
   }
-  return conv_plan_launch(u->ind_plan, s);
+  forward_tail(u, N, out, nullptr, s, &fl);   // compute flops first (plan cached on the second call)
+  rc = timed(true, fl, [&]() { return forward_tail(u, N, out, nullptr, s, nullptr); });
+  if (rc != KDIP_OK) return rc;
+  for (auto& op : u->bwd_ops) {
+    rc = timed(op.is_conv, op.flops, [&]() { return op(s); });
+    if (rc != KDIP_OK) return rc;
+  }
+  vjp_tail(u, N, grad_x, s, &fl);
+  rc = timed(true, fl, [&]() { return vjp_tail(u, N, grad_x, s, nullptr); });
+  if (rc != KDIP_OK) return rc;
+  KDIP_CUDA(cudaStreamSynchronize(s));
+  memset(prof, 0, sizeof(*prof));
+  for (auto& r : recs) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.a, r.b);
+    if (r.conv) { prof->conv_ms += ms; prof->conv_flops += r.flops; prof->conv_launches++; }
+    else { prof->other_ms += ms; prof->other_steps++; }
+  }
+  cudaEventElapsedTime(&prof->total_ms, recs.front().a, recs.back().b);
+  for (auto& r : recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  return KDIP_OK;
 }

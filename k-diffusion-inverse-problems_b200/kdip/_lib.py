@@ -30,9 +30,10 @@ def parse_header(path=HEADER):
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     src = re.sub(r"typedef\s+struct\s*\{.*?\}\s*\w+\s*;", "", src, flags=re.S)
     protos = {}
-    for m in re.finditer(r"(?:^|\n)\s*(const char\*|int|void)\s+(kdip_\w+)\s*\(([^;{]*?)\)\s*;", src):
+    for m in re.finditer(r"(?:^|\n)\s*(const char\*|unsigned long long|int|void)\s+(kdip_\w+)\s*\(([^;{]*?)\)\s*;", src):
         ret, name, args = m.group(1), m.group(2), m.group(3).strip()
-        restype = {"int": ctypes.c_int, "void": None, "const char*": ctypes.c_char_p}[ret]
+        restype = {"int": ctypes.c_int, "void": None, "const char*": ctypes.c_char_p,
+                   "unsigned long long": ctypes.c_ulonglong}[ret]
         argtypes = []
         if args and args != "void":
             for a in args.split(","):
@@ -74,7 +75,18 @@ def check(rc):
 
 
 class PmvScalars(ctypes.Structure):
-    _fields_ = [(n, ctypes.c_float) for n in ("c_in", "recip", "recipm1", "min_log", "max_log", "post_var", "inv_coef1_sq")]
+    _fields_ = [(n, ctypes.c_float) for n in ("c_in", "recip", "recipm1", "min_log", "max_log", "post_var", "coef1_sq")]
+
+
+class UNetProfile(ctypes.Structure):
+    _fields_ = [("conv_ms", ctypes.c_float), ("other_ms", ctypes.c_float), ("total_ms", ctypes.c_float),
+                ("conv_flops", ctypes.c_double), ("conv_launches", ctypes.c_int), ("other_steps", ctypes.c_int)]
+
+
+class OpDesc(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_int), ("S", ctypes.c_int), ("sf", ctypes.c_int), ("sigma_s", ctypes.c_float),
+                ("psf", ctypes.c_void_p), ("ksize", ctypes.c_int), ("mask", ctypes.c_void_p), ("rs_w", ctypes.c_void_p),
+                ("rs_idx", ctypes.c_void_p), ("rs_taps", ctypes.c_int)]
 
 
 class ConvSeg(ctypes.Structure):

@@ -1,0 +1,259 @@
+"""Thin Python handles over the libkdip C ABI for the guidance / operator / sampler kernels.
+
+Every function here launches hand-written CUDA through ctypes on torch's current stream; torch is used only to own
+device memory.  There is no CPU fallback: tensors must be CUDA fp32 contiguous (``_lib.ptr`` asserts it).
+"""
+import ctypes
+import warnings
+
+import numpy as np
+import torch
+
+from ._lib import KDIP_ENOTCONV, OpDesc, PmvScalars, check, lib, ptr, stream_ptr
+
+OP_KIND = {"inpainting": 0, "gaussian_blur": 1, "motion_blur": 2, "super_resolution": 3}
+OT_KIND = {None: 0, "dct": 1, "dwt": 2}
+
+
+def _f32(t):
+    return t.contiguous().float()
+
+
+class Workspace:
+    """A growable, 256-byte aligned device scratch buffer (a torch uint8 tensor)."""
+
+    def __init__(self, device):
+        self.device = device
+        self._buf = None
+
+    def get(self, nbytes):
+        if self._buf is None or self._buf.numel() < nbytes + 256:
+            self._buf = None
+            self._buf = torch.empty(nbytes + 256, dtype=torch.uint8, device=self.device)
+        off = (-self._buf.data_ptr()) % 256
+        return ctypes.c_void_p(self._buf.data_ptr() + off), self._buf.numel() - 256
+
+
+class OperatorHandle:
+    """Device-resident measurement operator (kdip_op_*): OTF / mask / Resizer tables live in the library."""
+
+    def __init__(self, kind, S, sigma_s, device, psf=None, mask=None, sf=1, resizer=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("kdip operators need a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.kind, self.S, self.sf, self.device = kind, int(S), int(sf), torch.device(device)
+        d = OpDesc()
+        d.kind, d.S, d.sf, d.sigma_s = OP_KIND[kind], int(S), int(sf), float(sigma_s)
+        keep = []
+        if psf is not None:
+            a = np.ascontiguousarray(psf, dtype=np.float32)
+            keep.append(a)
+            d.psf, d.ksize = a.ctypes.data, a.shape[-1]
+        if mask is not None:
+            m = np.ascontiguousarray(mask, dtype=np.float32).reshape(3, S, S)
+            keep.append(m)
+            d.mask = m.ctypes.data
+        if resizer is not None:
+            w, idx = resizer
+            w = np.ascontiguousarray(w, dtype=np.float32)
+            idx = np.ascontiguousarray(idx, dtype=np.int32)
+            keep += [w, idx]
+            d.rs_w, d.rs_idx, d.rs_taps = w.ctypes.data, idx.ctypes.data, w.shape[1]
+        h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            check(lib.kdip_op_create(ctypes.byref(d), ctypes.byref(h)))
+        self._h = h
+        self._ws = Workspace(self.device)
+        self._ws_bytes = {}
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            lib.kdip_op_destroy(h)
+            self._h = None
+
+    def _workspace(self, B):
+        if B not in self._ws_bytes:
+            n = ctypes.c_size_t()
+            check(lib.kdip_op_workspace_bytes(self._h, B, ctypes.byref(n)))
+            self._ws_bytes[B] = n.value
+        return self._ws.get(self._ws_bytes[B])
+
+    def out_hw(self):
+        return self.S // self.sf
+
+    def forward(self, x, noise=None):
+        x = _f32(x)
+        B = x.shape[0]
+        y = torch.empty(B, 3, self.out_hw(), self.out_hw(), device=x.device, dtype=torch.float32)
+        if noise is not None:
+            noise = _f32(noise)
+        ws, nb = self._workspace(B)
+        check(lib.kdip_op_forward(self._h, ptr(x), ptr(noise), ptr(y), B, ws, nb, stream_ptr()))
+        return y
+
+    def transpose(self, y):
+        y = _f32(y)
+        B = y.shape[0]
+        x = torch.empty(B, 3, self.S, self.S, device=y.device, dtype=torch.float32)
+        ws, nb = self._workspace(B)
+        check(lib.kdip_op_transpose(self._h, ptr(y), ptr(x), B, ws, nb, stream_ptr()))
+        return x
+
+    def otf(self):
+        fb = torch.empty(self.S, self.S, 2, device=self.device, dtype=torch.float32)
+        check(lib.kdip_op_otf(self._h, ptr(fb), stream_ptr()))
+        return torch.view_as_complex(fb)
+
+    def mat_closed(self, y, x0, theta):
+        """theta: [B] device tensor of scalar variances."""
+        y, x0, theta = _f32(y), _f32(x0), _f32(theta)
+        B = x0.shape[0]
+        mat = torch.empty_like(x0)
+        ws, nb = self._workspace(B)
+        check(lib.kdip_mat_closed(self._h, ptr(y), ptr(x0), ptr(theta), ptr(mat), B, ws, nb, stream_ptr()))
+        return mat
+
+    def mat_cg(self, y, x0, theta_map, ot=None, tol=1e-4, maxiter=1000):
+        y, x0, theta_map = _f32(y), _f32(x0), _f32(theta_map)
+        B = x0.shape[0]
+        mat = torch.empty_like(x0)
+        iters = (ctypes.c_int * B)()
+        ws, nb = self._workspace(B)
+        rc = lib.kdip_mat_cg(self._h, ptr(y), ptr(x0), ptr(theta_map), OT_KIND[ot], ptr(mat), B, tol, maxiter, iters, ws, nb,
+                             stream_ptr())
+        if rc == KDIP_ENOTCONV:
+            warnings.warn("CG not converge.")        # condition/condition.py:344-345: non-fatal
+        else:
+            check(rc)
+        self.last_cg_iters = list(iters)
+        return mat
+
+    def dps_grad(self, y, x0):
+        """-> (v = A^T (y - A x0) [B,3,S,S], norm [B] = ||y - A x0||_2)."""
+        y, x0 = _f32(y), _f32(x0)
+        B = x0.shape[0]
+        v = torch.empty_like(x0)
+        norm = torch.empty(B, device=x0.device, dtype=torch.float32)
+        ws, nb = self._workspace(B)
+        check(lib.kdip_dps_grad(self._h, ptr(y), ptr(x0), ptr(v), ptr(norm), B, ws, nb, stream_ptr()))
+        return v, norm
+
+
+_ortho_ws = {}
+
+
+def ortho(ot, x, inverse=False, mul=None):
+    """OrthoTransform kernels: out = mul .* W^T x (forward) or W x (inverse).  x [B,3,S,S]."""
+    x = _f32(x)
+    B, _, S, _ = x.shape
+    out = torch.empty_like(x)
+    if mul is not None:
+        mul = _f32(mul.expand_as(x))
+    n = ctypes.c_size_t()
+    check(lib.kdip_ortho_workspace_bytes(OT_KIND[ot], B, S, ctypes.byref(n)))
+    ws, nb = None, 0
+    if n.value:
+        w = _ortho_ws.setdefault(x.device, Workspace(x.device))
+        ws, nb = w.get(n.value)
+    check(lib.kdip_ortho(OT_KIND[ot], int(inverse), ptr(x), ptr(mul), ptr(out), B, S, ws, nb, stream_ptr()))
+    return out
+
+
+# ---- p_mean_variance epilogue / guidance combine -----------------------------------------------------------------------
+
+def pmv_scalars(diffusion, t, c_in, device):
+    """Per-image scalar table for the epilogue kernels from the float64 schedule at integer t
+    (gaussian_diffusion.py:895-908: numpy float64 -> fp32 at use).  t: list[int], c_in: list[float]."""
+    B = len(t)
+    arr = (PmvScalars * B)()
+    for b in range(B):
+        tb = int(t[b])
+        arr[b].c_in = float(np.float32(c_in[b]))
+        arr[b].recip = float(np.float32(diffusion.sqrt_recip_alphas_cumprod[tb]))
+        arr[b].recipm1 = float(np.float32(diffusion.sqrt_recipm1_alphas_cumprod[tb]))
+        arr[b].min_log = float(np.float32(diffusion.posterior_log_variance_clipped[tb]))
+        arr[b].max_log = float(np.float32(np.log(diffusion.betas[tb])))
+        arr[b].post_var = float(np.float32(diffusion.posterior_variance[tb]))
+        c1 = np.float32(diffusion.posterior_mean_coef1[tb])
+        arr[b].coef1_sq = float(c1 * c1)
+    host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+    return host.to(device, non_blocking=False)
+
+
+def pmv_epilogue(unet_out, x, sc, want_var):
+    B, _, H, W = x.shape
+    x0 = torch.empty_like(x)
+    var = torch.empty_like(x) if want_var else None
+    check(lib.kdip_pmv_epilogue(ptr(unet_out), ptr(x), ptr(sc), ptr(x0), ptr(var), B, H * W, stream_ptr()))
+    return x0, var
+
+
+def pmv_vjp_seed(x0_mean, v, sc):
+    B, _, H, W = x0_mean.shape
+    seed = torch.empty(B, 6, H, W, device=v.device, dtype=torch.float32)
+    direct = torch.empty_like(x0_mean)
+    check(lib.kdip_pmv_vjp_seed(ptr(x0_mean), ptr(_f32(v)), ptr(sc), ptr(seed), ptr(direct), B, H * W, stream_ptr()))
+    return seed, direct
+
+
+def guidance_combine(x0_mean, g, direct, coef, c_in=None, out=None):
+    B = x0_mean.shape[0]
+    chw = x0_mean[0].numel()
+    hat = torch.empty_like(x0_mean) if out is None else out
+    check(lib.kdip_guidance_combine(ptr(x0_mean), ptr(_f32(g)), ptr(direct), ptr(_f32(coef)), ptr(c_in), ptr(hat), B, chw,
+                                    stream_ptr()))
+    return hat
+
+
+def lincomb(x, y, a, c):
+    """out = a[b]*x + c[b]*y (per-image device scalars), unclipped."""
+    B = x.shape[0]
+    out = torch.empty_like(x)
+    check(lib.kdip_lincomb(ptr(_f32(x)), ptr(y), ptr(_f32(a)), ptr(c), ptr(out), B, x[0].numel(), stream_ptr()))
+    return out
+
+
+def v2_epilogue(unet_out, cov_out, x, sigma_dev, want_var):
+    """(x0_mean, x0_var, theta0_var) of ConditionOpenAIDenoiserV2.uncond_pred; variances None unless want_var."""
+    B, _, H, W = x.shape
+    x0 = torch.empty_like(x)
+    var = torch.empty_like(x) if want_var else None
+    var_ot = torch.empty_like(x) if want_var else None
+    check(lib.kdip_v2_epilogue(ptr(unet_out), ptr(cov_out), ptr(x), ptr(sigma_dev), ptr(x0), ptr(var), ptr(var_ot), B, H * W,
+                               stream_ptr()))
+    return x0, var, var_ot
+
+
+# ---- sampler updates -------------------------------------------------------------------------------------------------
+
+def churn_(x, noise, s_noise, sigma, sigma_hat):
+    check(lib.kdip_churn(ptr(x), ptr(_f32(noise)), float(s_noise), float(sigma), float(sigma_hat), x.numel(), stream_ptr()))
+    return x
+
+
+def euler_step(x, denoised, sigma_hat, dt, want_d=False):
+    x_out = torch.empty_like(x)
+    d = torch.empty_like(x) if want_d else None
+    check(lib.kdip_euler_step(ptr(x), ptr(_f32(denoised)), float(sigma_hat), float(dt), ptr(x_out), ptr(d), x.numel(), stream_ptr()))
+    return (x_out, d) if want_d else x_out
+
+
+def heun_step(x, d, x2, denoised2, sigma_next, dt):
+    x_out = torch.empty_like(x)
+    check(lib.kdip_heun_step(ptr(x), ptr(d), ptr(x2), ptr(_f32(denoised2)), float(sigma_next), float(dt), ptr(x_out), x.numel(),
+                             stream_ptr()))
+    return x_out
+
+
+def gather(src, idx):
+    B, M = src.shape[0], idx.numel()
+    dst = torch.empty(B, M, device=src.device, dtype=torch.float32)
+    check(lib.kdip_gather(ptr(_f32(src)), ptr(idx), ptr(dst), B, src[0].numel(), M, stream_ptr()))
+    return dst
+
+
+def scatter(src, idx, shape):
+    B = src.shape[0]
+    dst = torch.empty(B, *shape, device=src.device, dtype=torch.float32)
+    check(lib.kdip_scatter(ptr(_f32(src)), ptr(idx), ptr(dst), B, dst[0].numel(), idx.numel(), stream_ptr()))
+    return dst

@@ -53,6 +53,7 @@ class UNetEngine:
         self._ws = None
         self._ws_N = 0
         self._fwd_N = 0
+        self.forward_token = 0   # bumped by every forward: the VJP is only valid for the latest one
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -86,7 +87,32 @@ class UNetEngine:
         ws, ws_bytes = self._workspace(N)
         check(lib.kdip_unet_forward(self._h, ptr(x), ptr(x_scale), ptr(t), N, ptr(out), ptr(cov), ws, ws_bytes, stream_ptr()))
         self._fwd_N = N
+        self.forward_token += 1
         return (out, cov) if want_cov else out
+
+    def feature(self, N):
+        """Pre-head feature [N, C0, S, S] fp32 of the last forward (UNetModel.forward(return_feature=True))."""
+        assert N == self._fwd_N, "feature must follow forward with the same batch"
+        c0 = int(self.arch.channel_mult[0] * self.arch.model_channels)
+        feat = torch.empty(N, c0, self.image_size, self.image_size, device=self.device, dtype=torch.float32)
+        check(lib.kdip_unet_feature(self._h, N, ptr(feat), stream_ptr()))
+        return feat
+
+    def profile(self, x, t, seed, x_scale=None):
+        """Instrumented forward + VJP (kdip_unet_profile): per-class device times from CUDA events around every step."""
+        from ._lib import UNetProfile
+        N = x.shape[0]
+        x, seed = x.contiguous().float(), seed.contiguous().float()
+        t = t.to(self.device, torch.float32).contiguous()
+        out = torch.empty(N, 6, x.shape[2], x.shape[3], device=self.device, dtype=torch.float32)
+        g = torch.empty(N, 3, x.shape[2], x.shape[3], device=self.device, dtype=torch.float32)
+        ws, ws_bytes = self._workspace(N)
+        prof = UNetProfile()
+        check(lib.kdip_unet_profile(self._h, ptr(x), ptr(x_scale), ptr(t), ptr(seed), N, ptr(out), ptr(g), ws, ws_bytes,
+                                    stream_ptr(), ctypes.byref(prof)))
+        self._fwd_N = N
+        self.forward_token += 1
+        return {k: getattr(prof, k) for k, _ in UNetProfile._fields_}
 
     def vjp(self, seed, out=None):
         """seed [N,6,S,S] fp32 -> d<seed, unet_out>/d(unet_input) [N,3,S,S] fp32 for the preceding forward."""

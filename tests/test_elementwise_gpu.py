@@ -50,7 +50,7 @@ def _scalars(sched, sigma, t, B):
         arr[b].min_log = float(np.float32(sched.posterior_log_variance_clipped[t]))
         arr[b].max_log = float(np.float32(sched.log_betas[t]))
         arr[b].post_var = float(np.float32(sched.posterior_variance[t]))
-        arr[b].inv_coef1_sq = float(1.0 / np.float32(sched.posterior_mean_coef1[t]) ** 2)
+        arr[b].coef1_sq = float(np.float32(sched.posterior_mean_coef1[t]) ** 2)
     buf = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).cuda()
     return buf
 
