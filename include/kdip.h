@@ -65,12 +65,15 @@ typedef struct {
   float coef1_sq;      /* posterior_mean_coef1[t]^2 (fp32 square) condition.py:245               */
 } kdip_pmv_scalars;
 
+#define KDIP_VAR_MODEL 1   /* p_mean_variance's 'variance' (LEARNED_RANGE), gaussian_diffusion.py:271-276 */
+#define KDIP_VAR_CONVERT 2 /* Convert x0 variance, Eq. (22): clip((variance - post_var)/coef1_sq, 1e-6), condition.py:243-246 */
 /* unet_out [B,6,HW], x [B,3,HW] (UNSCALED x_t; the kernel applies c_in) ->
  *   x0_mean [B,3,HW] = clamp(recip*c_in*x - recipm1*eps, -1, 1)
- *   x0_var  [B,3,HW] (may be NULL) = clip((exp(frac*max_log+(1-frac)*min_log) - post_var)/coef1_sq, 1e-6)
+ *   x0_var  [B,3,HW] (may be NULL) = variance = exp(frac*max_log+(1-frac)*min_log), frac = (v+1)/2   (KDIP_VAR_MODEL)
+ *                                    or its Eq. (22) conversion                                    (KDIP_VAR_CONVERT)
  * sc: device array of B kdip_pmv_scalars. */
 int kdip_pmv_epilogue(const float* unet_out, const float* x, const kdip_pmv_scalars* sc, float* x0_mean, float* x0_var,
-                      int B, int HW, kdip_stream_t s);
+                      int var_mode, int B, int HW, kdip_stream_t s);
 /* VJP seed for the UNet output given v = d(loss)/d(x0_mean): writes seed [B,6,HW] = (-recipm1*m*v, 0) with
  * m = 1 where the clamp is inactive (x0_mean strictly inside (-1,1) reproduces torch.clamp's gradient), and
  * direct [B,3,HW] = recip*c_in*m*v (the d/dx of the explicit recip*c_in*x term). */

@@ -199,7 +199,7 @@ class ConditionOpenAIDenoiser(ConditionDenoiser):
         ct = self.x0_cov_type
         mle = bool(sig < self.mle_sigma_thres)
         sc = ops.pmv_scalars(self.diffusion, t_int, c_in, x.device)
-        x0_mean, var = ops.pmv_epilogue(out, x, sc, want_var=(ct == 'convert' and mle))
+        x0_mean, var = ops.pmv_epilogue(out, x, sc, ops.VAR_CONVERT if (ct == 'convert' and mle) else 0)
         self._ctx = dict(sc=sc, c_in_dev=c_in_dev, eng=eng, token=eng.forward_token)
         r2 = _dev([float(sig ** 2 / (1 + sig ** 2))] * B, x.device)
         if ct == 'convert':

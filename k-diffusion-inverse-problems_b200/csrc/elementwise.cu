@@ -60,7 +60,7 @@ __global__ void heun_kernel(const float* __restrict__ x, const float* __restrict
 // ---- p_mean_variance epilogue ----------------------------------------------------------------------------------------
 // grid.y = image; each thread handles 4 pixels of all 3 channels.
 __global__ void pmv_kernel(const float* __restrict__ out, const float* __restrict__ x, const kdip_pmv_scalars* __restrict__ sc,
-                           float* __restrict__ x0, float* __restrict__ var, int HW4) {
+                           float* __restrict__ x0, float* __restrict__ var, int convert, int HW4) {
   const int b = blockIdx.y;
   const kdip_pmv_scalars s = sc[b];
   const float a = s.recip * s.c_in;
@@ -79,11 +79,15 @@ __global__ void pmv_kernel(const float* __restrict__ out, const float* __restric
     if (var) {
       float4 v = ld4(ob + 3 * HW * 4, i), o;
       // variance = exp(frac*max_log + (1-frac)*min_log), frac = (v+1)/2 ; Convert: clip((variance - beta~)/coef1^2, 1e-6)
-      float f;
-      f = (v.x + 1.f) * 0.5f; o.x = fmaxf((expf(f * s.max_log + (1.f - f) * s.min_log) - s.post_var) / s.coef1_sq, 1e-6f);
-      f = (v.y + 1.f) * 0.5f; o.y = fmaxf((expf(f * s.max_log + (1.f - f) * s.min_log) - s.post_var) / s.coef1_sq, 1e-6f);
-      f = (v.z + 1.f) * 0.5f; o.z = fmaxf((expf(f * s.max_log + (1.f - f) * s.min_log) - s.post_var) / s.coef1_sq, 1e-6f);
-      f = (v.w + 1.f) * 0.5f; o.w = fmaxf((expf(f * s.max_log + (1.f - f) * s.min_log) - s.post_var) / s.coef1_sq, 1e-6f);
+      const float vv[4] = {v.x, v.y, v.z, v.w};
+      float r4[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float f = (vv[j] + 1.f) * 0.5f;
+        const float mv = expf(f * s.max_log + (1.f - f) * s.min_log);          // model variance, gaussian_diffusion.py:271-276
+        r4[j] = convert ? fmaxf((mv - s.post_var) / s.coef1_sq, 1e-6f) : mv;   // Eq. (22), condition.py:243-246
+      }
+      o = make_float4(r4[0], r4[1], r4[2], r4[3]);
       st4(var + (size_t)b * 3 * HW * 4, i, o);
     }
   }
@@ -250,10 +254,12 @@ static inline dim3 grid_by(int per_image_vec, int B) {
 }
 
 extern "C" int kdip_pmv_epilogue(const float* unet_out, const float* x, const kdip_pmv_scalars* sc, float* x0_mean,
-                                 float* x0_var, int B, int HW, kdip_stream_t s) {
+                                 float* x0_var, int var_mode, int B, int HW, kdip_stream_t s) {
   REQ_ALIGN16(unet_out); REQ_ALIGN16(x); REQ_ALIGN16(x0_mean); REQ_ALIGN16(x0_var); REQ_MULT4(HW);
   KDIP_REQUIRE(B > 0, KDIP_ESHAPE, "pmv_epilogue: B must be > 0");
-  pmv_kernel<<<grid_by(3 * HW / 4, B), EW_THREADS, 0, (cudaStream_t)s>>>(unet_out, x, sc, x0_mean, x0_var, HW / 4);
+  KDIP_REQUIRE(x0_var == nullptr || var_mode == KDIP_VAR_MODEL || var_mode == KDIP_VAR_CONVERT, KDIP_EINVAL, "pmv_epilogue: bad var_mode %d", var_mode);
+  pmv_kernel<<<grid_by(3 * HW / 4, B), EW_THREADS, 0, (cudaStream_t)s>>>(unet_out, x, sc, x0_mean, x0_var,
+                                                                         var_mode == KDIP_VAR_CONVERT ? 1 : 0, HW / 4);
   KDIP_LAUNCH_CHECK();
   return KDIP_OK;
 }

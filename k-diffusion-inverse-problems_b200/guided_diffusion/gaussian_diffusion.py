@@ -61,7 +61,8 @@ class _PmvEpilogue(th.autograd.Function):
 
     @staticmethod
     def forward(ctx, model_output, x, sc, want_var):
-        x0, var = ops.pmv_epilogue(model_output.contiguous().float(), x.contiguous().float(), sc, want_var)
+        x0, var = ops.pmv_epilogue(model_output.contiguous().float(), x.contiguous().float(), sc,
+                                   ops.VAR_MODEL if want_var else 0)
         ctx.sc = sc
         ctx.save_for_backward(x0)
         if var is None:

@@ -180,11 +180,15 @@ def pmv_scalars(diffusion, t, c_in, device):
     return host.to(device, non_blocking=False)
 
 
-def pmv_epilogue(unet_out, x, sc, want_var):
+VAR_MODEL, VAR_CONVERT = 1, 2
+
+
+def pmv_epilogue(unet_out, x, sc, var_mode=0):
+    """var_mode: 0 no variance, VAR_MODEL = p_mean_variance's variance, VAR_CONVERT = Eq. (22) x0 variance."""
     B, _, H, W = x.shape
     x0 = torch.empty_like(x)
-    var = torch.empty_like(x) if want_var else None
-    check(lib.kdip_pmv_epilogue(ptr(unet_out), ptr(x), ptr(sc), ptr(x0), ptr(var), B, H * W, stream_ptr()))
+    var = torch.empty_like(x) if var_mode else None
+    check(lib.kdip_pmv_epilogue(ptr(unet_out), ptr(x), ptr(sc), ptr(x0), ptr(var), int(var_mode), B, H * W, stream_ptr()))
     return x0, var
 
 

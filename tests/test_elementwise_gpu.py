@@ -71,13 +71,16 @@ def test_pmv_epilogue_and_vjp_seed(sigma):
     x0, var = torch.empty(B, 3, HW, device="cuda"), torch.empty(B, 3, HW, device="cuda")
     st = stream_ptr()
     out_c, x_c = out.cuda(), x.cuda()
-    check(lib.kdip_pmv_epilogue(ptr(out_c), ptr(x_c), ptr(sc), ptr(x0), ptr(var), B, HW, st))
+    check(lib.kdip_pmv_epilogue(ptr(out_c), ptr(x_c), ptr(sc), ptr(x0), ptr(var), 2, B, HW, st))
     assert torch.allclose(x0.cpu().view_as(x0_ref), x0_ref, rtol=1e-5, atol=2e-6)
     # Eq. 22 subtracts two nearly equal variances and divides by coef1^2 (tiny at large t): an ulp of exp() is amplified
     # by 1/coef1^2, so the absolute tolerance is 8 ulp(variance) * 1/coef1^2 (conditioning of the formula, not the kernel).
     amp = float(1.0 / np.float32(sched.posterior_mean_coef1[t]) ** 2)
     atol = 8 * 1.2e-7 * float(var_ref.max()) * amp
     assert torch.allclose(var.cpu().view_as(conv_ref), conv_ref, rtol=2e-4, atol=atol), (atol, (var.cpu().view_as(conv_ref) - conv_ref).abs().max())
+    raw = torch.empty(B, 3, HW, device="cuda")
+    check(lib.kdip_pmv_epilogue(ptr(out_c), ptr(x_c), ptr(sc), ptr(x0), ptr(raw), 1, B, HW, st))
+    assert torch.allclose(raw.cpu().view_as(var_ref), var_ref, rtol=2e-6, atol=0)      # model variance: 1-2 ulp of exp
     # VJP seed vs autograd through the oracle epilogue
     v = _mk(B, 3, HW, seed=3)
     xo = x.clone().requires_grad_()

@@ -45,6 +45,15 @@ def cpu_noise(shape, seed=2):
     return torch.randn(*shape)
 
 
+def ref_noise(name, ref, x0, seed=2):
+    """The measurement noise the reference drew after torch.manual_seed(seed): randn_like(y) fills in y's MEMORY order,
+    and the Resizer's output is a transposed (non-contiguous) tensor, so the SR draw must reuse the oracle's strides."""
+    torch.manual_seed(seed)
+    if name == "super_resolution":
+        return torch.randn_like(ref.down_sample(x0)).contiguous()
+    return torch.randn(*x0.shape)
+
+
 @pytest.mark.parametrize("size", [64, 256])
 @pytest.mark.parametrize("name", NAMES)
 def test_operator_forward_transpose_closed_form(name, size, golden_small):
@@ -53,8 +62,7 @@ def test_operator_forward_transpose_closed_form(name, size, golden_small):
     sub = I.sub if size == 256 else (lambda a: a)
     op, ref = make_op(name, size), make_ref(name, size)
     x0 = I.image(size, batch=1, seed=1)
-    yshape = (1, 3, size // 4, size // 4) if name == "super_resolution" else (1, 3, size, size)
-    noise = cpu_noise(yshape)                                    # the reference's torch.manual_seed(2) draw
+    noise = ref_noise(name, ref, x0)                             # the reference's torch.manual_seed(2) draw
     y = op.handle.forward(x0.cuda(), noise.cuda())
     assert rel(sub(y.cpu()), G[f"op{size}.{name}.y"]) < 2e-5
     y0 = op.forward(x0.cuda(), noiseless=True)
@@ -86,8 +94,7 @@ def test_cg_mat(name, ot, golden_small):
     G = golden_small
     op, ref = make_op(name, 64), make_ref(name, 64)
     x0 = I.image(64, batch=1, seed=1)
-    yshape = (1, 3, 16, 16) if name == "super_resolution" else (1, 3, 64, 64)
-    y_ref = ref.forward(x0, noise=cpu_noise(yshape))
+    y_ref = ref.forward(x0, noise=ref_noise(name, ref, x0))
     xm = I.image(64, batch=1, seed=4) * 0.8
     th = I.theta_map(64, seed=5)
     mat = __MAT_SOLVER__[name](op, y_ref.cuda(), xm.cuda(), th.cuda(), OrthoTransform(ot))
