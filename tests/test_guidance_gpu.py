@@ -87,7 +87,9 @@ def test_guided_eval(combo, tiny_model, golden_small):
     print(f"guided eval {opname}/{guidance}/{cov}/{sigma}: max {e_max:.3e} l2 {e_l2:.3e}")
     assert torch.isfinite(hat).all()
     gold = golden_small[f"guid.{opname}.{guidance}.{cov}.{sigma}"]
-    if not (e_max < 6e-2 and e_l2 < 3e-2):
+    well = e_max < 6e-2 and e_l2 < 3e-2
+    s_l2 = 0.0
+    if not well:
         # ill-conditioned case: measure the reference's own sensitivity to bf16 weight rounding (module docstring)
         from oracle import guidance_ref
         cfg, sd_b = bf16_weight_oracle()
@@ -103,8 +105,11 @@ def test_guided_eval(combo, tiny_model, golden_small):
                                   measurement=measurement(op, opname, batch=3), guidance=guidance, device="cuda",
                                   mle_sigma_thres=0.2, **extra).eval()
     hat3 = cm3(xt.expand(3, -1, -1, -1).contiguous(), torch.full((3,), sigma).cuda())
-    if cov != "tmpd":
-        assert errs(hat3[2:3], hat)[0] < 2e-2
+    b_max, b_l2 = errs(hat3[2:3], hat)
+    print(f"   batch-of-3 vs single: max {b_max:.3e} l2 {b_l2:.3e}")
+    # only the accumulation order of the GroupNorm statistics differs between the two runs (atomics): bf16-level noise,
+    # amplified like any other perturbation in the ill-conditioned cases
+    assert b_l2 <= (1e-2 if well else 2 * s_l2)
 
 
 @pytest.mark.parametrize("run", I.SAMPLER_RUNS, ids=lambda r: r[0])
