@@ -94,7 +94,7 @@ struct kdip_unet {
   std::vector<void*> owned;                    // cudaMalloc'ed by create
   std::vector<ResWeights> resw;                // per plan entry (unused entries for other kinds)
   std::vector<AttnWeights> attw;
-  float *w_in_small = nullptr, *w_headd_small = nullptr;   // direct-conv weights [9][CIN][C]
+  bf16 *w_in_i2c = nullptr, *w_headd_i2c = nullptr;        // im2col GEMM weights [C0][64] (first conv, head input-gradient)
   bf16 *w_ind = nullptr, *w_head = nullptr, *w_cov = nullptr;
   const float *b_in = nullptr, *b_head = nullptr, *b_cov = nullptr, *g_head = nullptr, *be_head = nullptr;
   float *wall = nullptr, *ball = nullptr;      // concatenated emb_layers
@@ -291,8 +291,9 @@ extern "C" int kdip_unet_create(const kdip_unet_arch* arch, int n_tensors, const
     if (b.kind == 0) {
       const float* w;
       TRY(get(p + ".weight", (int64_t)b.cout * 3 * 9, &w));
-      TRY(dev_alloc(u, (size_t)9 * 3 * b.cout * 4, (void**)&u->w_in_small));
-      TRY(launch_pack_small(w, b.cout, 3, 0, u->w_in_small, s));
+      if (b.cout % 64 != 0) { set_error("unet_create: first conv width %d must be a multiple of 64", b.cout); return fail(KDIP_ESHAPE); }
+      TRY(dev_alloc(u, (size_t)b.cout * 64 * 2, (void**)&u->w_in_i2c));
+      TRY(launch_pack_im2col_weight(w, b.cout, 3, 0, b.cout, u->w_in_i2c, s));
       TRY(keep(p + ".bias", b.cout, &u->b_in));
       TRY(pack(p + ".weight", b.cout, 3, 0, 3, 9, 1, &u->w_ind));   // dgrad: rows = 3 (pad 16), cols = cout
     } else if (b.kind == 1) {
@@ -360,8 +361,8 @@ extern "C" int kdip_unet_create(const kdip_unet_arch* arch, int n_tensors, const
     u->b_head = hb16;
     const float* hw;
     TRY(get("out.2.weight", (int64_t)6 * c0 * 9, &hw));
-    TRY(dev_alloc(u, (size_t)9 * 6 * c0 * 4, (void**)&u->w_headd_small));
-    TRY(launch_pack_small(hw, 6, c0, 1, u->w_headd_small, s));
+    TRY(dev_alloc(u, (size_t)c0 * 64 * 2, (void**)&u->w_headd_i2c));
+    TRY(launch_pack_im2col_weight(hw, 6, c0, 1, c0, u->w_headd_i2c, s));
     // optional DWT-Var covariance head (k_diffusion/external.py:141): Conv2d(C, 6, 1) on the pre-head feature
     if (src.count("out_cov.weight")) {
       TRY(pack("out_cov.weight", 6, c0, 0, c0, 1, 0, &u->w_cov));
@@ -551,10 +552,15 @@ static int build_launch_plan(kdip_unet* u, int N, void* ws, size_t ws_bytes, siz
       h = B.new_act(H, H, b.cout);
       h.stats = take_stats(b.cout);
       if (emit) {
-        kdip_unet* uu = u; Act o = h; int n = N, hh = H, co = b.cout;
-        F.push_back([=](cudaStream_t s) {
-          return launch_conv_small_cin(uu->io_x, uu->io_xscale, uu->w_in_small, uu->b_in, n, 3, hh, hh, co, o.p, s);
-        });
+        // first conv (unet.py:484): im2col of the (scaled) fp32 input into scrB, then a K=64 1x1 implicit GEMM
+        kdip_unet* uu = u; int n = N, hh = H;
+        F.push_back([=](cudaStream_t s) { return launch_im2col3x3(uu->io_x, uu->io_xscale, n, 3, hh, hh, scrB, s); });
+        kdip_conv_desc d0;
+        memset(&d0, 0, sizeof(d0));
+        d0.N = N; d0.H = H; d0.W = H; d0.Cout_pad = b.cout; d0.Cout = b.cout; d0.nseg = 1;
+        d0.seg[0].act = scrB; d0.seg[0].C = 64; d0.seg[0].wgt = u->w_in_i2c; d0.seg[0].taps = 1;
+        d0.bias = u->b_in; d0.out = h.p; d0.out_mode = 0; d0.out_scale = 1.f;
+        add_conv_op(F, conv(d0));
       }
       stats_op(F, h);
       rec.in0 = h;
@@ -691,10 +697,19 @@ static int build_launch_plan(kdip_unet* u, int N, void* ws, size_t ws_bytes, siz
       // head: seed (fp32 NCHW, 6 ch) -> g_a (g2) via direct dgrad; GN(+SiLU) backward -> gin
       float* red = take_red(c0);
       int hh = H;
+      // head input-gradient (unet.py:617): im2col of the fp32 seed into g3, then a K=64 1x1 implicit GEMM -> g2
       K.push_back([=](cudaStream_t s) {
         KDIP_CUDA(cudaMemsetAsync(uu->red_base, 0, uu->red_bytes, s));
-        return launch_conv_small_cin(uu->io_seed, nullptr, uu->w_headd_small, nullptr, n, 6, hh, hh, c0, g2, s);
+        return launch_im2col3x3(uu->io_seed, nullptr, n, 6, hh, hh, g3, s);
       });
+      {
+        kdip_conv_desc dh;
+        memset(&dh, 0, sizeof(dh));
+        dh.N = N; dh.H = H; dh.W = H; dh.Cout_pad = c0; dh.Cout = c0; dh.nseg = 1;
+        dh.seg[0].act = g3; dh.seg[0].C = 64; dh.seg[0].wgt = u->w_headd_i2c; dh.seg[0].taps = 1;
+        dh.out = g2; dh.out_mode = 0; dh.out_scale = 1.f;
+        add_conv_op(K, conv(dh));
+      }
       K.push_back([=](cudaStream_t s) { return launch_gn_bwd_reduce(hlast.p, c0, nullptr, 0, n, hh, hh, ab_head, 1, RS_NONE, g2, red, s); });
       K.push_back([=](cudaStream_t s) { return launch_gn_bwd_finalize(red, ab_head, mr_head, nullptr, n, c0, hh * hh, nullptr, 0, 0, kbuf, s); });
       K.push_back([=](cudaStream_t s) { return launch_gn_bwd_apply(hlast.p, c0, nullptr, 0, n, hh, hh, ab_head, kbuf, 1, RS_NONE, g2, nullptr, 0, gin, nullptr, s); });

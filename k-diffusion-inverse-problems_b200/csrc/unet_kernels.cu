@@ -135,74 +135,159 @@ int launch_gn_finalize(const float* stats0, int C0, const float* stats1, int C1,
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// GroupNorm apply (+SiLU, + resample)
+// GroupNorm apply / backward: "channel-stationary" streaming kernels.
+// A thread owns one 8-channel vector (16 B of bf16) of image n and walks over pixels, so the per-(image, channel) affine
+// coefficients live in registers for the whole kernel and every iteration is one 16 B load, ~6 ALU ops + 1 MUFU per element
+// and one 16 B store; 4 independent loads are in flight per thread.  SiLU uses tanh.approx (rel. error 2^-11, below the bf16
+// rounding of the stored result): silu(u) = h + h*tanh(h), h = u/2.
 // ---------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ V8 affine_act(const V8& x, const float* __restrict__ abp, int act_silu) {
-  V8 r;
-  const float4* q = reinterpret_cast<const float4*>(abp);
-  float4 a0 = __ldg(q), a1 = __ldg(q + 1), a2 = __ldg(q + 2), a3 = __ldg(q + 3);
-  const float A[8] = {a0.x, a0.z, a1.x, a1.z, a2.x, a2.z, a3.x, a3.z};
-  const float B[8] = {a0.y, a0.w, a1.y, a1.w, a2.y, a2.w, a3.y, a3.w};
+__device__ __forceinline__ float fast_tanh(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float silu_fast(float u) {
+  const float h = 0.5f * u;
+  return fmaf(h, fast_tanh(h), h);
+}
+// d/du silu(u) = s*(1 + u*(1-s)), s = sigmoid(u) = 0.5 + 0.5*tanh(u/2)
+__device__ __forceinline__ float dsilu_fast(float u) {
+  const float s = fmaf(0.5f, fast_tanh(0.5f * u), 0.5f);
+  return s * fmaf(u, 1.f - s, 1.f);
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 u;
+  u.x = pack_bf16(f[0], f[1]); u.y = pack_bf16(f[2], f[3]); u.z = pack_bf16(f[4], f[5]); u.w = pack_bf16(f[6], f[7]);
+  return u;
+}
+__device__ __forceinline__ uint4 ldv(const bf16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ void stv(bf16* p, const uint4& v) { *reinterpret_cast<uint4*>(p) = v; }
+
+// per-thread view of a (possibly two-source) NHWC tensor restricted to this thread's 8 channels of image n
+struct ChanView {
+  const bf16* base;   // points at [n][pixel 0][c0] of the source holding channel c0
+  int stride;         // channels of that source
+};
+__device__ __forceinline__ ChanView chan_view(const bf16* s0, int C0, const bf16* s1, int C1, int n, int P, int c0) {
+  ChanView v;
+  if (c0 < C0) { v.base = s0 + (size_t)n * P * C0 + c0; v.stride = C0; }
+  else { v.base = s1 + (size_t)n * P * C1 + (c0 - C0); v.stride = C1; }
+  return v;
+}
+// (A, B) pairs of 8 consecutive channels: ab[(n*C + c0)*2 ...]
+__device__ __forceinline__ void load_ab(const float* __restrict__ ab, int n, int C, int c0, float (&A)[8], float (&B)[8]) {
+  const float4* q = reinterpret_cast<const float4*>(ab + ((size_t)n * C + c0) * 2);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float4 t = __ldg(q + j);
+    A[2 * j] = t.x; B[2 * j] = t.y; A[2 * j + 1] = t.z; B[2 * j + 1] = t.w;
+  }
+}
+
+template <bool SILU>
+__device__ __forceinline__ void affine8(const uint4& raw, const float (&A)[8], const float (&B)[8], float (&r)[8]) {
+  float x[8];
+  unpack8(raw, x);
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    float u = A[j] * x.v[j] + B[j];
-    r.v[j] = act_silu ? silu_f(u) : u;
+    const float u = fmaf(A[j], x[j], B[j]);
+    r[j] = SILU ? silu_fast(u) : u;
   }
-  return r;
 }
 
-__global__ void gn_apply_kernel(const bf16* __restrict__ s0, int C0, const bf16* __restrict__ s1, int C1, int N, int H, int W,
-                                const float* __restrict__ ab, int act_silu, int resample, bf16* __restrict__ out) {
-  const int C = C0 + C1;
-  const int vec = C >> 3;
-  const int Ho = resample == RS_AVGPOOL2 ? H / 2 : (resample == RS_NEAREST_UP2 ? H * 2 : H);
-  const int Wo = resample == RS_AVGPOOL2 ? W / 2 : (resample == RS_NEAREST_UP2 ? W * 2 : W);
-  const size_t total = (size_t)N * Ho * Wo * vec;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int v = (int)(i % vec);
-    const size_t po = i / vec;
-    const int xo = (int)(po % Wo);
-    const int yo = (int)((po / Wo) % Ho);
-    const int n = (int)(po / ((size_t)Wo * Ho));
-    const int c0 = v * 8;
-    const float* abp = ab + ((size_t)n * C + c0) * 2;
-    V8 r;
-    if (resample == RS_NONE) {
-      r = affine_act(ld_bf16x8(src_ptr(s0, C0, s1, C1, ((size_t)n * H + yo) * W + xo, c0)), abp, act_silu);
-    } else if (resample == RS_NEAREST_UP2) {
-      r = affine_act(ld_bf16x8(src_ptr(s0, C0, s1, C1, ((size_t)n * H + (yo >> 1)) * W + (xo >> 1), c0)), abp, act_silu);
-    } else {
+static constexpr int GN_THREADS = 256;
+static constexpr int GN_UNROLL = 4;
+
+// y = resample(act(A*x + B)).  Iterates over output pixels (RS_NONE, RS_AVGPOOL2) or input pixels (RS_NEAREST_UP2: the
+// activation is evaluated once and stored to the 2x2 replicas).
+template <int RS, bool SILU>
+__global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const bf16* __restrict__ s0, int C0, const bf16* __restrict__ s1, int C1,
+                                                              int H, int W, const float* __restrict__ ab, bf16* __restrict__ out,
+                                                              int pix_per_block) {
+  const int C = C0 + C1, vec = C >> 3;
+  const int rows = GN_THREADS / vec;
+  const int cv = threadIdx.x % vec, row = threadIdx.x / vec;
+  if (row >= rows) return;
+  const int n = blockIdx.y, c0 = cv * 8;
+  float A[8], B[8];
+  load_ab(ab, n, C, c0, A, B);
+  const ChanView in = chan_view(s0, C0, s1, C1, n, H * W, c0);
+  const int Ho = RS == RS_AVGPOOL2 ? H / 2 : (RS == RS_NEAREST_UP2 ? H * 2 : H);
+  const int Wo = RS == RS_AVGPOOL2 ? W / 2 : (RS == RS_NEAREST_UP2 ? W * 2 : W);
+  bf16* dst = out + (size_t)n * Ho * Wo * C + c0;
+  const int Pit = RS == RS_NEAREST_UP2 ? H * W : Ho * Wo;       // iteration space
+  const int p_end = min(Pit, (int)(blockIdx.x + 1) * pix_per_block);
+  int p = blockIdx.x * pix_per_block + row;
+  if (RS == RS_NONE) {
+    for (; p + (GN_UNROLL - 1) * rows < p_end; p += GN_UNROLL * rows) {
+      uint4 v[GN_UNROLL];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) r.v[j] = 0.f;
+      for (int k = 0; k < GN_UNROLL; ++k) v[k] = ldv(in.base + (size_t)(p + k * rows) * in.stride);
 #pragma unroll
-      for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-        for (int dx = 0; dx < 2; ++dx) {
-          V8 t = affine_act(ld_bf16x8(src_ptr(s0, C0, s1, C1, ((size_t)n * H + 2 * yo + dy) * W + 2 * xo + dx, c0)), abp, act_silu);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) r.v[j] += t.v[j];
-        }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) r.v[j] *= 0.25f;
+      for (int k = 0; k < GN_UNROLL; ++k) {
+        float r[8];
+        affine8<SILU>(v[k], A, B, r);
+        stv(dst + (size_t)(p + k * rows) * C, pack8(r));
+      }
     }
-    st_bf16x8(out + po * C + c0, r);
+    for (; p < p_end; p += rows) {
+      float r[8];
+      affine8<SILU>(ldv(in.base + (size_t)p * in.stride), A, B, r);
+      stv(dst + (size_t)p * C, pack8(r));
+    }
+  } else if (RS == RS_AVGPOOL2) {
+    for (; p < p_end; p += rows) {
+      const int yo = p / Wo, xo = p - yo * Wo;
+      const bf16* q = in.base + ((size_t)(2 * yo) * W + 2 * xo) * in.stride;
+      const uint4 v0 = ldv(q), v1 = ldv(q + in.stride), v2 = ldv(q + (size_t)W * in.stride), v3 = ldv(q + (size_t)(W + 1) * in.stride);
+      float r0[8], r1[8], r2[8], r3[8], r[8];
+      affine8<SILU>(v0, A, B, r0); affine8<SILU>(v1, A, B, r1); affine8<SILU>(v2, A, B, r2); affine8<SILU>(v3, A, B, r3);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = 0.25f * ((r0[j] + r1[j]) + (r2[j] + r3[j]));
+      stv(dst + (size_t)p * C, pack8(r));
+    }
+  } else {
+    for (; p < p_end; p += rows) {
+      const int y = p / W, x = p - y * W;
+      float r[8];
+      affine8<SILU>(ldv(in.base + (size_t)p * in.stride), A, B, r);
+      const uint4 o = pack8(r);
+      bf16* d = dst + ((size_t)(2 * y) * Wo + 2 * x) * C;
+      stv(d, o); stv(d + C, o); stv(d + (size_t)Wo * C, o); stv(d + (size_t)(Wo + 1) * C, o);
+    }
   }
 }
 
-static inline int ew_blocks(size_t total, int threads) {
-  size_t b = (total + threads - 1) / threads;
-  size_t cap = (size_t)num_sms() * 16;
-  return (int)(b < cap ? (b ? b : 1) : cap);
+// grid.x so that ~8 CTAs per SM are resident across the batch; every CTA gets a contiguous pixel range of one image
+static inline void gn_grid(int N, int P, int rows, dim3* grid, int* pix_per_block) {
+  int bx = (num_sms() * 8 + N - 1) / N;
+  int ppb = (P + bx - 1) / bx;
+  const int quantum = rows * GN_UNROLL;
+  ppb = ((ppb + quantum - 1) / quantum) * quantum;
+  if (ppb < quantum) ppb = quantum;
+  *pix_per_block = ppb;
+  *grid = dim3((P + ppb - 1) / ppb, N);
 }
 
 int launch_gn_apply(const bf16* src0, int C0, const bf16* src1, int C1, int N, int H, int W, const float* ab, int act_silu,
                     int resample, bf16* out, cudaStream_t s) {
-  KDIP_REQUIRE(C0 % 8 == 0 && C1 % 8 == 0, KDIP_ESHAPE, "gn_apply: channels must be multiples of 8");
+  const int C = C0 + C1;
+  KDIP_REQUIRE(C0 % 8 == 0 && C1 % 8 == 0 && C / 8 <= GN_THREADS && C > 0, KDIP_ESHAPE, "gn_apply: channels %d+%d unsupported", C0, C1);
   KDIP_REQUIRE(resample != RS_AVGPOOL2 || (H % 2 == 0 && W % 2 == 0), KDIP_ESHAPE, "gn_apply: avg-pool needs even H, W");
-  const int Ho = resample == RS_AVGPOOL2 ? H / 2 : (resample == RS_NEAREST_UP2 ? H * 2 : H);
-  const int Wo = resample == RS_AVGPOOL2 ? W / 2 : (resample == RS_NEAREST_UP2 ? W * 2 : W);
-  size_t total = (size_t)N * Ho * Wo * ((C0 + C1) / 8);
-  gn_apply_kernel<<<ew_blocks(total, 256), 256, 0, s>>>(src0, C0, src1, C1, N, H, W, ab, act_silu, resample, out);
+  const int rows = GN_THREADS / (C / 8);
+  const int Pit = resample == RS_AVGPOOL2 ? (H / 2) * (W / 2) : H * W;
+  dim3 grid;
+  int ppb;
+  gn_grid(N, Pit, rows, &grid, &ppb);
+#define GN_APPLY(RS, SL) gn_apply_kernel<RS, SL><<<grid, GN_THREADS, 0, s>>>(src0, C0, src1, C1, H, W, ab, out, ppb)
+  if (resample == RS_NONE) { if (act_silu) GN_APPLY(RS_NONE, true); else GN_APPLY(RS_NONE, false); }
+  else if (resample == RS_AVGPOOL2) { if (act_silu) GN_APPLY(RS_AVGPOOL2, true); else GN_APPLY(RS_AVGPOOL2, false); }
+  else { if (act_silu) GN_APPLY(RS_NEAREST_UP2, true); else GN_APPLY(RS_NEAREST_UP2, false); }
+#undef GN_APPLY
   KDIP_LAUNCH_CHECK();
   return KDIP_OK;
 }
@@ -210,72 +295,78 @@ int launch_gn_apply(const bf16* src0, int C0, const bf16* src1, int C1, int N, i
 // ---------------------------------------------------------------------------------------------------------------------
 // GroupNorm backward
 // ---------------------------------------------------------------------------------------------------------------------
-// g_u at input pixel (n,y,x), channels c0..c0+7: resample^T(g_y) * act'(u)
-__device__ __forceinline__ V8 grad_u(const V8& xv, const float* __restrict__ abp, int act_silu, int resample,
-                                     const bf16* __restrict__ gy, int n, int y, int x, int H, int W, int C, int c0) {
-  V8 g;
-  if (resample == RS_NONE) {
-    g = ld_bf16x8(gy + (((size_t)n * H + y) * W + x) * C + c0);
-  } else if (resample == RS_AVGPOOL2) {
-    g = ld_bf16x8(gy + (((size_t)n * (H / 2) + (y >> 1)) * (W / 2) + (x >> 1)) * C + c0);
+// g_u at input pixel p = (y, x) of image n for this thread's 8 channels: resample^T(g_y) * act'(A*x + B)
+template <int RS, bool SILU>
+__device__ __forceinline__ void grad_u8(const uint4& xraw, const float (&A)[8], const float (&B)[8], const bf16* __restrict__ gyb,
+                                        int y, int x, int H, int W, int C, float (&xf)[8], float (&g)[8]) {
+  unpack8(xraw, xf);
+  if (RS == RS_NONE) {
+    unpack8(ldv(gyb + ((size_t)y * W + x) * C), g);
+  } else if (RS == RS_AVGPOOL2) {
+    unpack8(ldv(gyb + ((size_t)(y >> 1) * (W >> 1) + (x >> 1)) * C), g);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) g.v[j] *= 0.25f;
+    for (int j = 0; j < 8; ++j) g[j] *= 0.25f;
   } else {
+    const bf16* q = gyb + ((size_t)(2 * y) * (2 * W) + 2 * x) * C;
+    float a[8], b[8], c[8], d[8];
+    unpack8(ldv(q), a); unpack8(ldv(q + C), b); unpack8(ldv(q + (size_t)2 * W * C), c); unpack8(ldv(q + (size_t)(2 * W + 1) * C), d);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) g.v[j] = 0.f;
-#pragma unroll
-    for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-      for (int dx = 0; dx < 2; ++dx) {
-        V8 t = ld_bf16x8(gy + (((size_t)n * (2 * H) + 2 * y + dy) * (2 * W) + 2 * x + dx) * C + c0);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) g.v[j] += t.v[j];
-      }
+    for (int j = 0; j < 8; ++j) g[j] = (a[j] + b[j]) + (c[j] + d[j]);
   }
-  if (act_silu) {
-    const float4* q = reinterpret_cast<const float4*>(abp);
-    float4 a0 = __ldg(q), a1 = __ldg(q + 1), a2 = __ldg(q + 2), a3 = __ldg(q + 3);
-    const float A[8] = {a0.x, a0.z, a1.x, a1.z, a2.x, a2.z, a3.x, a3.z};
-    const float B[8] = {a0.y, a0.w, a1.y, a1.w, a2.y, a2.w, a3.y, a3.w};
+  if (SILU) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) g.v[j] *= dsilu_f(A[j] * xv.v[j] + B[j]);
+    for (int j = 0; j < 8; ++j) g[j] *= dsilu_fast(fmaf(A[j], xf[j], B[j]));
   }
-  return g;
 }
 
-__global__ void gn_bwd_reduce_kernel(const bf16* __restrict__ s0, int C0, const bf16* __restrict__ s1, int C1, int H, int W,
-                                     const float* __restrict__ ab, int act_silu, int resample, const bf16* __restrict__ gy,
-                                     int rows_per_block, float* __restrict__ red_out) {
-  extern __shared__ float red[];
-  const int C = C0 + C1;
-  const int vec = C >> 3;
-  const int rpp = blockDim.x / vec;
-  const int col = threadIdx.x % vec;
-  const int row = threadIdx.x / vec;
-  const int n = blockIdx.y;
-  const int P = H * W;
-  const int p0 = blockIdx.x * rows_per_block;
-  const int p1 = min(P, p0 + rows_per_block);
+template <int RS, bool SILU>
+__global__ void __launch_bounds__(GN_THREADS) gn_bwd_reduce_kernel(const bf16* __restrict__ s0, int C0, const bf16* __restrict__ s1,
+                                                                   int C1, int H, int W, const float* __restrict__ ab,
+                                                                   const bf16* __restrict__ gy, int pix_per_block,
+                                                                   float* __restrict__ red_out) {
+  extern __shared__ float red[];   // [rows][vec*16]
+  const int C = C0 + C1, vec = C >> 3;
+  const int rows = GN_THREADS / vec;
+  const int cv = threadIdx.x % vec, row = threadIdx.x / vec;
+  const int n = blockIdx.y, c0 = cv * 8, P = H * W;
   float r1[8], r2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) r1[j] = r2[j] = 0.f;
-  if (row < rpp) {
-    const int c0 = col * 8;
-    const float* abp = ab + ((size_t)n * C + c0) * 2;
-    for (int p = p0 + row; p < p1; p += rpp) {
-      const int y = p / W, x = p % W;
-      V8 xv = ld_bf16x8(src_ptr(s0, C0, s1, C1, (size_t)n * P + p, c0));
-      V8 g = grad_u(xv, abp, act_silu, resample, gy, n, y, x, H, W, C, c0);
+  if (row < rows) {
+    float A[8], B[8];
+    load_ab(ab, n, C, c0, A, B);
+    const ChanView in = chan_view(s0, C0, s1, C1, n, P, c0);
+    const int Pg = RS == RS_AVGPOOL2 ? P / 4 : (RS == RS_NEAREST_UP2 ? P * 4 : P);
+    const bf16* gyb = gy + (size_t)n * Pg * C + c0;
+    const int p_end = min(P, (int)(blockIdx.x + 1) * pix_per_block);
+    int p = blockIdx.x * pix_per_block + row;
+    for (; p + (GN_UNROLL - 1) * rows < p_end; p += GN_UNROLL * rows) {
+      uint4 v[GN_UNROLL];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { r1[j] += g.v[j]; r2[j] += g.v[j] * xv.v[j]; }
+      for (int k = 0; k < GN_UNROLL; ++k) v[k] = ldv(in.base + (size_t)(p + k * rows) * in.stride);
+#pragma unroll
+      for (int k = 0; k < GN_UNROLL; ++k) {
+        const int pp = p + k * rows, y = pp / W, x = pp - y * W;
+        float xf[8], g[8];
+        grad_u8<RS, SILU>(v[k], A, B, gyb, y, x, H, W, C, xf, g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { r1[j] += g[j]; r2[j] = fmaf(g[j], xf[j], r2[j]); }
+      }
+    }
+    for (; p < p_end; p += rows) {
+      const int y = p / W, x = p - y * W;
+      float xf[8], g[8];
+      grad_u8<RS, SILU>(ldv(in.base + (size_t)p * in.stride), A, B, gyb, y, x, H, W, C, xf, g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { r1[j] += g[j]; r2[j] = fmaf(g[j], xf[j], r2[j]); }
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { red[(row * vec + col) * 16 + j] = r1[j]; red[(row * vec + col) * 16 + 8 + j] = r2[j]; }
+    for (int j = 0; j < 8; ++j) { red[(row * vec + cv) * 16 + j] = r1[j]; red[(row * vec + cv) * 16 + 8 + j] = r2[j]; }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < vec * 16; i += blockDim.x) {
     float acc = 0.f;
-    for (int r = 0; r < rpp; ++r) acc += red[r * vec * 16 + i];
+    for (int r = 0; r < rows; ++r) acc += red[r * vec * 16 + i];
     const int c = (i >> 4) * 8 + (i & 7);
     const int which = (i >> 3) & 1;
     atomicAdd(red_out + ((size_t)n * C + c) * 2 + which, acc);
@@ -285,15 +376,17 @@ __global__ void gn_bwd_reduce_kernel(const bf16* __restrict__ s0, int C0, const 
 int launch_gn_bwd_reduce(const bf16* src0, int C0, const bf16* src1, int C1, int N, int H, int W, const float* ab, int act_silu,
                          int resample, const bf16* gy, float* red, cudaStream_t s) {
   const int C = C0 + C1;
-  KDIP_REQUIRE(C % 8 == 0 && C / 8 <= 256 && C0 % 8 == 0, KDIP_ESHAPE, "gn_bwd_reduce: C=%d unsupported", C);
-  const int vec = C / 8, rpp = 256 / vec, P = H * W;
-  int target_blocks = (num_sms() * 4 + N - 1) / N;
-  int rows = (P + target_blocks - 1) / target_blocks;
-  if (rows < rpp * 4) rows = rpp * 4;
-  if (rows > P) rows = P;
-  dim3 grid((P + rows - 1) / rows, N);
-  size_t smem = (size_t)rpp * vec * 16 * sizeof(float);
-  gn_bwd_reduce_kernel<<<grid, 256, smem, s>>>(src0, C0, src1, C1, H, W, ab, act_silu, resample, gy, rows, red);
+  KDIP_REQUIRE(C0 % 8 == 0 && C1 % 8 == 0 && C / 8 <= GN_THREADS && C > 0, KDIP_ESHAPE, "gn_bwd_reduce: channels %d+%d unsupported", C0, C1);
+  const int vec = C / 8, rows = GN_THREADS / vec;
+  dim3 grid;
+  int ppb;
+  gn_grid(N, H * W, rows, &grid, &ppb);
+  const size_t smem = (size_t)rows * vec * 16 * sizeof(float);
+#define GN_RED(RS, SL) gn_bwd_reduce_kernel<RS, SL><<<grid, GN_THREADS, smem, s>>>(src0, C0, src1, C1, H, W, ab, gy, ppb, red)
+  if (resample == RS_NONE) { if (act_silu) GN_RED(RS_NONE, true); else GN_RED(RS_NONE, false); }
+  else if (resample == RS_AVGPOOL2) { if (act_silu) GN_RED(RS_AVGPOOL2, true); else GN_RED(RS_AVGPOOL2, false); }
+  else { if (act_silu) GN_RED(RS_NEAREST_UP2, true); else GN_RED(RS_NEAREST_UP2, false); }
+#undef GN_RED
   KDIP_LAUNCH_CHECK();
   return KDIP_OK;
 }
@@ -336,52 +429,85 @@ int launch_gn_bwd_finalize(const float* red, const float* ab, const float* mr, c
   return KDIP_OK;
 }
 
-__global__ void gn_bwd_apply_kernel(const bf16* __restrict__ s0, int C0, const bf16* __restrict__ s1, int C1, int N, int H, int W,
-                                    const float* __restrict__ ab, const float* __restrict__ k, int act_silu, int resample,
-                                    const bf16* __restrict__ gy, const bf16* __restrict__ extra, int extra_mode,
-                                    bf16* __restrict__ d0, bf16* __restrict__ d1) {
-  const int C = C0 + C1;
-  const int vec = C >> 3;
-  const size_t total = (size_t)N * H * W * vec;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int v = (int)(i % vec);
-    const size_t np = i / vec;
-    const int x = (int)(np % W);
-    const int y = (int)((np / W) % H);
-    const int n = (int)(np / ((size_t)W * H));
-    const int c0 = v * 8;
-    const float* abp = ab + ((size_t)n * C + c0) * 2;
-    V8 xv = ld_bf16x8(src_ptr(s0, C0, s1, C1, np, c0));
-    V8 g = grad_u(xv, abp, act_silu, resample, gy, n, y, x, H, W, C, c0);
+// g_x = k0*g_u + k1 + k2*x (+ extra), written per source (the concat's two gradients go to two tensors)
+template <int RS, bool SILU, int EXTRA>
+__global__ void __launch_bounds__(GN_THREADS) gn_bwd_apply_kernel(const bf16* __restrict__ s0, int C0, const bf16* __restrict__ s1,
+                                                                  int C1, int H, int W, const float* __restrict__ ab,
+                                                                  const float* __restrict__ k, const bf16* __restrict__ gy,
+                                                                  const bf16* __restrict__ extra, int pix_per_block,
+                                                                  bf16* __restrict__ d0, bf16* __restrict__ d1) {
+  const int C = C0 + C1, vec = C >> 3;
+  const int rows = GN_THREADS / vec;
+  const int cv = threadIdx.x % vec, row = threadIdx.x / vec;
+  if (row >= rows) return;
+  const int n = blockIdx.y, c0 = cv * 8, P = H * W;
+  float A[8], B[8], K1[8], K2[8];
+  load_ab(ab, n, C, c0, A, B);
+  {
     const float4* kq = reinterpret_cast<const float4*>(k + ((size_t)n * C + c0) * 4);
-    V8 r;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float4 kk = __ldg(kq + j);
-      r.v[j] = kk.x * g.v[j] + kk.y + kk.z * xv.v[j];
+      const float4 kk = __ldg(kq + j);
+      K1[j] = kk.y; K2[j] = kk.z;       // kk.x == A[j]
     }
-    if (extra_mode == 1) {
-      V8 e = ld_bf16x8(extra + np * C + c0);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) r.v[j] += e.v[j];
-    } else if (extra_mode == 2) {
-      V8 e = grad_u(xv, abp, 0, resample, extra, n, y, x, H, W, C, c0);   // plain resample^T, no activation factor
-#pragma unroll
-      for (int j = 0; j < 8; ++j) r.v[j] += e.v[j];
-    }
-    bf16* dst = (c0 < C0) ? d0 + np * C0 + c0 : d1 + np * C1 + (c0 - C0);
-    st_bf16x8(dst, r);
   }
+  const ChanView in = chan_view(s0, C0, s1, C1, n, P, c0);
+  const int Pg = RS == RS_AVGPOOL2 ? P / 4 : (RS == RS_NEAREST_UP2 ? P * 4 : P);
+  const bf16* gyb = gy + (size_t)n * Pg * C + c0;
+  const bf16* exb = nullptr;
+  if (EXTRA == 1) exb = extra + (size_t)n * P * C + c0;
+  if (EXTRA == 2) exb = extra + (size_t)n * Pg * C + c0;
+  bf16* dst = (c0 < C0) ? d0 + (size_t)n * P * C0 + c0 : d1 + (size_t)n * P * C1 + (c0 - C0);
+  const int Cd = (c0 < C0) ? C0 : C1;
+  const int p_end = min(P, (int)(blockIdx.x + 1) * pix_per_block);
+  int p = blockIdx.x * pix_per_block + row;
+  auto body = [&](const uint4& xraw, int pp) {
+    const int y = pp / W, x = pp - y * W;
+    float xf[8], g[8], r[8];
+    grad_u8<RS, SILU>(xraw, A, B, gyb, y, x, H, W, C, xf, g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = fmaf(A[j], g[j], fmaf(K2[j], xf[j], K1[j]));
+    if (EXTRA == 1) {
+      float e[8];
+      unpack8(ldv(exb + (size_t)pp * C), e);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] += e[j];
+    } else if (EXTRA == 2) {
+      float e[8], dummy[8];
+      grad_u8<RS, false>(xraw, A, B, exb, y, x, H, W, C, dummy, e);     // plain resample^T, no activation factor
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] += e[j];
+    }
+    stv(dst + (size_t)pp * Cd, pack8(r));
+  };
+  for (; p + (GN_UNROLL - 1) * rows < p_end; p += GN_UNROLL * rows) {
+    uint4 v[GN_UNROLL];
+#pragma unroll
+    for (int kk = 0; kk < GN_UNROLL; ++kk) v[kk] = ldv(in.base + (size_t)(p + kk * rows) * in.stride);
+#pragma unroll
+    for (int kk = 0; kk < GN_UNROLL; ++kk) body(v[kk], p + kk * rows);
+  }
+  for (; p < p_end; p += rows) body(ldv(in.base + (size_t)p * in.stride), p);
 }
 
 int launch_gn_bwd_apply(const bf16* src0, int C0, const bf16* src1, int C1, int N, int H, int W, const float* ab,
                         const float* k, int act_silu, int resample, const bf16* gy, const bf16* extra, int extra_mode,
                         bf16* dst0, bf16* dst1, cudaStream_t s) {
-  KDIP_REQUIRE(C0 % 8 == 0 && C1 % 8 == 0, KDIP_ESHAPE, "gn_bwd_apply: channels must be multiples of 8");
+  const int C = C0 + C1;
+  KDIP_REQUIRE(C0 % 8 == 0 && C1 % 8 == 0 && C / 8 <= GN_THREADS && C > 0, KDIP_ESHAPE, "gn_bwd_apply: channels %d+%d unsupported", C0, C1);
   KDIP_REQUIRE(extra_mode == 0 || extra != nullptr, KDIP_EINVAL, "gn_bwd_apply: extra_mode set without tensor");
-  size_t total = (size_t)N * H * W * ((C0 + C1) / 8);
-  gn_bwd_apply_kernel<<<ew_blocks(total, 256), 256, 0, s>>>(src0, C0, src1, C1, N, H, W, ab, k, act_silu, resample, gy, extra,
-                                                            extra_mode, dst0, dst1);
+  KDIP_REQUIRE(extra_mode >= 0 && extra_mode <= 2, KDIP_EINVAL, "gn_bwd_apply: bad extra_mode %d", extra_mode);
+  const int rows = GN_THREADS / (C / 8);
+  dim3 grid;
+  int ppb;
+  gn_grid(N, H * W, rows, &grid, &ppb);
+#define GN_BA(RS, SL, EX) gn_bwd_apply_kernel<RS, SL, EX><<<grid, GN_THREADS, 0, s>>>(src0, C0, src1, C1, H, W, ab, k, gy, extra, ppb, dst0, dst1)
+#define GN_BA_EX(RS, SL) do { if (extra_mode == 0) GN_BA(RS, SL, 0); else if (extra_mode == 1) GN_BA(RS, SL, 1); else GN_BA(RS, SL, 2); } while (0)
+  if (resample == RS_NONE) { if (act_silu) GN_BA_EX(RS_NONE, true); else GN_BA_EX(RS_NONE, false); }
+  else if (resample == RS_AVGPOOL2) { if (act_silu) GN_BA_EX(RS_AVGPOOL2, true); else GN_BA_EX(RS_AVGPOOL2, false); }
+  else { if (act_silu) GN_BA_EX(RS_NEAREST_UP2, true); else GN_BA_EX(RS_NEAREST_UP2, false); }
+#undef GN_BA_EX
+#undef GN_BA
   KDIP_LAUNCH_CHECK();
   return KDIP_OK;
 }
@@ -393,6 +519,12 @@ int launch_axpy_f32(float* y, const float* x, float alpha, int n, cudaStream_t s
   axpy_f32_kernel<<<(n + 255) / 256, 256, 0, s>>>(y, x, alpha, n);
   KDIP_LAUNCH_CHECK();
   return KDIP_OK;
+}
+
+static inline int ew_blocks(size_t total, int threads) {
+  size_t b = (total + threads - 1) / threads;
+  size_t cap = (size_t)num_sms() * 16;
+  return (int)(b < cap ? (b ? b : 1) : cap);
 }
 
 __global__ void add_bf16_kernel(bf16* __restrict__ a, const bf16* __restrict__ b, size_t n8) {
@@ -474,6 +606,64 @@ int launch_conv_small_cin(const float* in, const float* in_scale, const float* w
     }
     conv_small_cin_kernel<6><<<(int)blocks, 256, smem, s>>>(in, in_scale, w, bias, N, H, W, Cout, out);
   }
+  KDIP_LAUNCH_CHECK();
+  return KDIP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// im2col for the two 3x3 convs with a tiny input-channel count (first conv 3->C0, head input-gradient 6->C0): the 9*CIN
+// taps of every pixel become one 64-channel bf16 NHWC row, so the conv runs on the tensor cores as a 1x1 implicit GEMM
+// with K = 64 (csrc/conv_gemm.cu) instead of a CUDA-core direct conv.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void im2col3x3_kernel(const float* __restrict__ in, const float* __restrict__ in_scale, int CIN, int H, int W,
+                                 bf16* __restrict__ out, size_t total) {
+  // one thread = one pixel x 8 of the 64 im2col channels
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int v = (int)(i & 7);
+    const size_t pix = i >> 3;
+    const int x = (int)(pix % W), y = (int)((pix / W) % H);
+    const size_t n = pix / ((size_t)W * H);
+    const float sc = in_scale ? __ldg(in_scale + n) : 1.f;
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = v * 8 + j;
+      float val = 0.f;
+      if (k < 9 * CIN) {
+        const int tap = k / CIN, ci = k - tap * CIN;
+        const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) val = __ldg(in + ((n * CIN + ci) * H + yy) * W + xx) * sc;
+      }
+      f[j] = val;
+    }
+    stv(out + pix * 64 + v * 8, pack8(f));
+  }
+}
+int launch_im2col3x3(const float* in, const float* in_scale, int N, int CIN, int H, int W, bf16* out, cudaStream_t s) {
+  KDIP_REQUIRE(9 * CIN <= 64, KDIP_ESHAPE, "im2col3x3: 9*CIN=%d exceeds the 64-channel row", 9 * CIN);
+  const size_t total = (size_t)N * H * W * 8;
+  im2col3x3_kernel<<<ew_blocks(total, 256), 256, 0, s>>>(in, in_scale, CIN, H, W, out, total);
+  KDIP_LAUNCH_CHECK();
+  return KDIP_OK;
+}
+// weights for the im2col GEMM: dst bf16 [rows_pad][64], row = output channel of the GEMM, col = tap*CIN + ci.
+// flip=0: conv O<-I forward: dst[o][tap*I + i] = w[o][i][tap].           (CIN = I, rows = O)
+// flip=1: input-gradient of a conv whose OUTPUT has few channels (head): dst[i][tap*O + o] = w[o][i][8 - tap]   (CIN = O, rows = I)
+__global__ void pack_im2col_weight_kernel(const float* __restrict__ w, int O, int I, int flip, int rows_pad, bf16* __restrict__ dst) {
+  const int total = rows_pad * 64;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int row = idx >> 6, col = idx & 63;
+    const int CIN = flip ? O : I, rows = flip ? I : O;
+    float v = 0.f;
+    if (row < rows && col < 9 * CIN) {
+      const int tap = col / CIN, c = col - tap * CIN;
+      v = flip ? w[((size_t)c * I + row) * 9 + (8 - tap)] : w[((size_t)row * I + c) * 9 + tap];
+    }
+    dst[idx] = __float2bfloat16(v);
+  }
+}
+int launch_pack_im2col_weight(const float* w_oihw, int O, int I, int flip, int rows_pad, bf16* dst, cudaStream_t s) {
+  pack_im2col_weight_kernel<<<64, 256, 0, s>>>(w_oihw, O, I, flip, rows_pad, dst);
   KDIP_LAUNCH_CHECK();
   return KDIP_OK;
 }

@@ -49,6 +49,11 @@ int launch_conv_small_cin(const float* in, const float* in_scale, const float* w
 // (input-gradient of a conv whose OUTPUT has few channels, e.g. the UNet head).
 int launch_pack_small(const float* w_oihw, int O, int I, int flip, float* dst, cudaStream_t s);
 
+// im2col of a 3x3 / pad-1 neighbourhood for CIN <= 7 input channels: in fp32 NCHW (times in_scale[n]) -> out bf16 [N,H,W,64]
+// with channel tap*CIN + ci (zero beyond 9*CIN and outside the image); and the matching GEMM weights [rows_pad][64].
+int launch_im2col3x3(const float* in, const float* in_scale, int N, int CIN, int H, int W, bf16* out, cudaStream_t s);
+int launch_pack_im2col_weight(const float* w_oihw, int O, int I, int flip, int rows_pad, bf16* dst, cudaStream_t s);
+
 // timestep embedding (nn.py:103-121) + time_embed MLP (unet.py:473-477): semb[N][ted] = SiLU(W2 SiLU(W1 e(t) + b1) + b2)
 int launch_time_embed(const float* t, int N, int mc, const float* w1, const float* b1, const float* w2, const float* b2,
                       float* semb, cudaStream_t s);
