@@ -12,8 +12,12 @@
 //   tap's weight slab — into a ring of 128B-swizzled shared-memory stages.
 // Math: one elected thread issues tcgen05.mma (M=128, N=BN, K=16, bf16 x bf16 -> fp32) with the accumulator in
 //   TMEM, double-buffered so the epilogue of tile i overlaps the main loop of tile i+1 (persistent CTAs).
-// Epilogue (4 warps = 128 TMEM lanes): tcgen05.ld -> +bias -> +residual (identity / 2x2 avg-pool / nearest-up
-//   skip paths of unet.py:190-197,257) -> bf16 NHWC or fp32 NCHW store (+ optional per-channel GroupNorm sums).
+// Epilogue, bf16 NHWC outputs with BN >= 64 (every ResBlock / attention conv): 8 warps, two per TMEM lane quadrant, each
+//   owning a 64-channel slab.  tcgen05.ld (2 x 32 columns in flight) -> +bias (shared memory) -> + identity residual (its
+//   tile is TMA-loaded by a dedicated producer thread, unet.py:257,306) -> bf16 -> 128B-swizzled staging tile in shared
+//   memory -> TMA store (cp.async.bulk.tensor, full 128 B lines; no scattered per-lane sectors).
+// Legacy epilogue (4 warps, per-lane global loads/stores) for the rare shapes: fp32 NCHW outputs with <= 32 channels (head,
+//   input gradient), 2x2 avg-pool / nearest-up skip paths (unet.py:190-197), fused channel statistics.
 #include "kdip_common.cuh"
 
 namespace kdip {
@@ -21,12 +25,18 @@ namespace kdip {
 static constexpr int kBlockM = 128;
 static constexpr int kBlockK = 64;                      // bf16 elements = 128 bytes = one swizzle row
 static constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KiB
-static constexpr int kThreads = 256;
+static constexpr int kThreads = 384;                    // 4 control warps + 8 epilogue warps
+static constexpr int kEpiThreads = 256;
+static constexpr int kSlabBytes = kBlockM * 128;        // one 64-channel bf16 slab of the output tile: 16 KiB
+static constexpr int kStagingBytes = 2 * kSlabBytes;    // 128 channels at a time
 static constexpr int kMaxStages = 8;
 
 struct ConvParams {
   CUtensorMap mapA[3];
   CUtensorMap mapB[3];
+  CUtensorMap mapOut;   // bf16 NHWC output, box {64, TW, TH, TN} (TMA-store epilogue)
+  CUtensorMap mapRes;   // identity residual, same geometry
+  int tma_epilogue;     // 1: 8-warp TMA-store epilogue; 0: legacy 4-warp epilogue
   int seg_taps[3];
   int seg_chunks[3];
   int nseg;
@@ -76,11 +86,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
 
   const int stage_bytes = kABytes + p.BN * 128;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.num_stages * stage_bytes);
+  uint8_t* staging = smem + p.num_stages * stage_bytes;                       // [2][128 rows][128 B], TMA-store source
+  uint8_t* res_stage = staging + (p.tma_epilogue ? kStagingBytes : 0);        // residual tile, same layout
+  uint8_t* after = res_stage + ((p.tma_epilogue && p.res_mode == 1) ? kStagingBytes : 0);
+  float* bias_s = reinterpret_cast<float*>(after);                            // [256]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(after + 1024);
   uint64_t* empty_bar = full_bar + kMaxStages;
   uint64_t* tmem_full_bar = empty_bar + kMaxStages;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* res_full_bar = tmem_empty_bar + 2;
+  uint64_t* res_empty_bar = res_full_bar + 1;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_empty_bar + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -90,6 +106,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       tma_prefetch_desc(&p.mapA[s]);
       tma_prefetch_desc(&p.mapB[s]);
     }
+    if (p.tma_epilogue) {
+      tma_prefetch_desc(&p.mapOut);
+      if (p.res_mode == 1) tma_prefetch_desc(&p.mapRes);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.num_stages; ++s) {
@@ -98,8 +118,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
-      mbar_init(&tmem_empty_bar[a], 128);
+      mbar_init(&tmem_empty_bar[a], p.tma_epilogue ? kEpiThreads : 128);
     }
+    mbar_init(res_full_bar, 1);
+    mbar_init(res_empty_bar, kEpiThreads);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -169,8 +191,96 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else if (warp >= 4) {
-    // ===================== epilogue: 4 warps, warp q owns TMEM lanes [32q, 32q+32) =====================
+  } else if (warp == 3) {
+    // ===================== residual producer: TMA-loads the identity-skip tile of every output tile =====================
+    if (lane == 0 && p.tma_epilogue && p.res_mode == 1) {
+      const int n_slabs = p.BN / 64;
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile);
+        for (int s0 = 0; s0 < n_slabs; s0 += 2, ++it) {
+          const int ns = (n_slabs - s0) < 2 ? (n_slabs - s0) : 2;
+          mbar_wait(res_empty_bar, (it & 1) ^ 1);
+          mbar_arrive_expect_tx(res_full_bar, (uint32_t)(ns * kSlabBytes));
+          for (int j = 0; j < ns; ++j)
+            tma_load_4d(res_stage + j * kSlabBytes, &p.mapRes, res_full_bar, t.nn0 + (s0 + j) * 64, t.x0, t.y0, t.n0);
+        }
+      }
+    }
+  } else if (warp >= 4 && p.tma_epilogue) {
+    // ===================== epilogue (TMA store): 8 warps; warp (q, g) owns TMEM lanes [32q, 32q+32) x slab g =====================
+    const int q = warp & 3;
+    const int g = (warp - 4) >> 2;
+    const int row = q * 32 + lane;
+    const int epi_tid = threadIdx.x - 128;
+    const int n_slabs = p.BN / 64;
+    const uint32_t swz = (uint32_t)(row & 7);
+    int acc = 0;
+    uint32_t acc_phase = 0, res_it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile);
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
+      for (int s0 = 0; s0 < n_slabs; s0 += 2) {
+        const bool active = (s0 + g) < n_slabs;
+        uint32_t v0[32], v1[32];
+        if (active) {
+          tmem_ld_32x32(t_row + (uint32_t)((s0 + g) * 64), v0);
+          tmem_ld_32x32(t_row + (uint32_t)((s0 + g) * 64 + 32), v1);
+          tmem_ld_wait();
+        }
+        if (s0 + 2 >= n_slabs) {   // last TMEM read of this tile: hand the accumulator back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(&tmem_empty_bar[acc]);
+        }
+        // the staging tile (and bias_s) may be rewritten once the previous TMA store has finished reading it
+        if (epi_tid == 0) tma_store_wait_read();
+        if (p.bias != nullptr && epi_tid < 128 && s0 * 64 + epi_tid < p.BN) bias_s[epi_tid] = __ldg(p.bias + t.nn0 + s0 * 64 + epi_tid);
+        named_bar_sync(1, kEpiThreads);
+        if (p.res_mode == 1) {
+          mbar_wait(res_full_bar, res_it & 1);
+          ++res_it;
+        }
+        if (active) {
+          uint8_t* dst_row = staging + g * kSlabBytes + row * 128;
+          const uint8_t* res_row = res_stage + g * kSlabBytes + row * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {     // 8 chunks of 8 channels (16 B)
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(j < 4 ? v0[j * 8 + e] : v1[(j - 4) * 8 + e]);
+            if (p.bias != nullptr) {
+              const float4 b0 = *reinterpret_cast<const float4*>(bias_s + g * 64 + j * 8);
+              const float4 b1 = *reinterpret_cast<const float4*>(bias_s + g * 64 + j * 8 + 4);
+              f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w; f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+            }
+            const uint32_t off = ((uint32_t)j ^ swz) << 4;
+            if (p.res_mode == 1) {
+              const uint4 ru = *reinterpret_cast<const uint4*>(res_row + off);
+              const float2 r0 = unpack_bf16(ru.x), r1 = unpack_bf16(ru.y), r2 = unpack_bf16(ru.z), r3 = unpack_bf16(ru.w);
+              f[0] += r0.x; f[1] += r0.y; f[2] += r1.x; f[3] += r1.y; f[4] += r2.x; f[5] += r2.y; f[6] += r3.x; f[7] += r3.y;
+            }
+            uint4 u;
+            u.x = pack_bf16(f[0], f[1]); u.y = pack_bf16(f[2], f[3]); u.z = pack_bf16(f[4], f[5]); u.w = pack_bf16(f[6], f[7]);
+            *reinterpret_cast<uint4*>(dst_row + off) = u;
+          }
+          fence_proxy_async();   // make the staging writes visible to the TMA (async proxy)
+        }
+        if (p.res_mode == 1) mbar_arrive(res_empty_bar);
+        named_bar_sync(2, kEpiThreads);
+        if (epi_tid == 0) {
+          const int ns = (n_slabs - s0) < 2 ? (n_slabs - s0) : 2;
+          for (int j = 0; j < ns; ++j)
+            tma_store_4d(staging + j * kSlabBytes, &p.mapOut, t.nn0 + (s0 + j) * 64, t.x0, t.y0, t.n0);
+          tma_store_commit();
+        }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (epi_tid == 0) tma_store_wait_all();
+  } else if (warp >= 4 && warp < 8) {
+    // ===================== legacy epilogue: 4 warps, warp q owns TMEM lanes [32q, 32q+32) =====================
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int tw = row % p.TW;
@@ -376,13 +486,29 @@ int conv_plan_build(const kdip_conv_desc* d, ConvPlan* plan) {
     if (rc != KDIP_OK) return rc;
   }
 
+  // TMA-store epilogue for bf16 NHWC outputs in 64-channel slabs without pooled / upsampled skips or fused statistics
+  p.tma_epilogue = (d->out_mode == 0 && BN >= 64 && d->Cout == d->Cout_pad && (d->res_mode == 0 || d->res_mode == 1) &&
+                    d->chan_stats == nullptr) ? 1 : 0;
+  int extra = 1024 /*bias + barriers*/;
+  if (p.tma_epilogue) {
+    extra += kStagingBytes + (d->res_mode == 1 ? kStagingBytes : 0);
+    int rc = encode_tmap_bf16_4d(&p.mapOut, d->out, (uint64_t)d->Cout, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N, 64,
+                                 (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TN);
+    if (rc != KDIP_OK) return rc;
+    if (d->res_mode == 1) {
+      KDIP_REQUIRE(((uintptr_t)d->residual % 16) == 0, KDIP_EALIGN, "conv: residual must be 16B aligned");
+      rc = encode_tmap_bf16_4d(&p.mapRes, d->residual, (uint64_t)d->Cout, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N, 64,
+                               (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TN);
+      if (rc != KDIP_OK) return rc;
+    }
+  }
   const int stage_bytes = kABytes + BN * 128;
-  const int budget = 200 * 1024;
+  const int budget = 227 * 1024 - extra - 1024 /*align slack*/ - 256;
   int stages = budget / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
-  if (stages < 2) stages = 2;
+  KDIP_REQUIRE(stages >= 2, KDIP_ESHAPE, "conv: not enough shared memory for a 2-stage pipeline (BN=%d)", BN);
   p.num_stages = stages;
-  plan->smem_bytes = (size_t)stages * stage_bytes + 1024 /*align slack*/ + (2 * kMaxStages + 4) * 8 + 16;
+  plan->smem_bytes = (size_t)stages * stage_bytes + 1024 /*align slack*/ + extra + 256;
   int sms = num_sms();
   plan->grid = p.total_tiles < sms ? p.total_tiles : sms;
   return KDIP_OK;

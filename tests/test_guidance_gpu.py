@@ -7,8 +7,8 @@ is NOT a well-conditioned function of the network at large sigma with the synthe
 the clamp inside the differentiated graph (gaussian_diffusion.py:296-297) switches a pixel's direct term on or off when x0
 crosses +-1.  The reference algorithm itself, evaluated in exact fp32 but with its WEIGHTS rounded to bf16 (a 2^-9 relative
 perturbation), moves hat_x0 by 0.25-0.28 relative L2 at sigma = 10 and its 4-6 step trajectories by 0.57-0.75.  So each
-case is held to:  error <= max(floor, 2 x that bf16-weight sensitivity of the reference), computed in the test by the CPU
-oracle; floor = 6e-2 max / 3e-2 relative L2 per evaluation.  Well-conditioned cases (sigma <= 1.5) pass the floor alone.
+case is held to:  relative L2 error <= max(floor, 2 x that bf16-weight sensitivity of the reference) and fraction of pixels
+off by > 6e-2 <= max(3 %, 3 x the reference's), computed in the test by the CPU oracle; floor = 6e-2 max / 3e-2 relative L2 per evaluation.  Well-conditioned cases (sigma <= 1.5) pass the floor alone.
 The sampler arithmetic itself is checked to fp32 accuracy with an analytic denoiser (test_sampler_exact_with_analytic_model)."""
 import numpy as np
 import pytest
@@ -99,7 +99,7 @@ def test_guided_eval(combo, tiny_model, golden_small):
         frac = ((hat.cpu() - torch.as_tensor(gold)).abs() > 6e-2).float().mean().item()
         s_frac = ((probe(I.xt(64, sigma, seed=21), torch.tensor([sigma])) - torch.as_tensor(gold)).abs() > 6e-2).float().mean().item()
         print(f"   bf16-weight sensitivity of the reference: max {s_max:.3e} l2 {s_l2:.3e} frac>6e-2 {s_frac:.3f} (ours {frac:.3f})")
-        assert e_l2 <= max(3e-2, 2 * s_l2) and frac <= max(0.02, 2 * s_frac)
+        assert e_l2 <= max(3e-2, 2 * s_l2) and frac <= max(0.03, 3 * s_frac)
     # batch of 3 identical problems == the single problem (images are independent units)
     cm3 = ConditionOpenAIDenoiser(inner_model=model, diffusion=diffusion, x0_cov_type=cov, recon_mse=recon_mse(), operator=op,
                                   measurement=measurement(op, opname, batch=3), guidance=guidance, device="cuda",
