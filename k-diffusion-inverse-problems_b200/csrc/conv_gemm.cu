@@ -37,6 +37,9 @@ struct ConvParams {
   CUtensorMap mapOut;   // bf16 NHWC output, box {64, TW, TH, TN} (TMA-store epilogue)
   CUtensorMap mapRes;   // identity residual, same geometry
   int tma_epilogue;     // 1: 8-warp TMA-store epilogue; 0: legacy 4-warp epilogue
+  int pair;             // 1: CTA pairs (cta_group::2, M = 256 per pair, B split across the two CTAs)
+  int b_rows;           // weight rows each CTA loads per k-block: BN (single) or BN/2 (pair)
+  int total_work;       // persistent-loop trip count: tiles (single) or pair tiles (pair)
   int seg_taps[3];
   int seg_chunks[3];
   int nseg;
@@ -79,13 +82,24 @@ __device__ __forceinline__ void load8_bf16(const __nv_bfloat16* p, float (&f)[8]
   f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
 }
 
+// work item -> tile index of this CTA.  Pair mode: work = pm * n_tiles + nt covers M-tiles 2pm (leader) and 2pm+1 (peer).
+__device__ __forceinline__ int work_to_tile(const ConvParams& p, int work, int rank) {
+  if (!p.pair) return work;
+  const int nt = work % p.n_tiles, pm = work / p.n_tiles;
+  return (2 * pm + rank) * p.n_tiles + nt;
+}
+
+template <bool kPair>
 __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment required by the 128B swizzle atoms (TMA destination and UMMA descriptors)
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
 
-  const int stage_bytes = kABytes + p.BN * 128;
+  const int stage_bytes = kABytes + p.b_rows * 128;
+  const int rank = kPair ? (int)cluster_ctarank() : 0;
+  const int work0 = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int work_stride = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   uint8_t* staging = smem + p.num_stages * stage_bytes;                       // [2][128 rows][128 B], TMA-store source
   uint8_t* res_stage = staging + (p.tma_epilogue ? kStagingBytes : 0);        // residual tile, same layout
   uint8_t* after = res_stage + ((p.tma_epilogue && p.res_mode == 1) ? kStagingBytes : 0);
@@ -113,23 +127,24 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.num_stages; ++s) {
-      mbar_init(&full_bar[s], 1);
+      mbar_init(&full_bar[s], kPair ? 2 : 1);   // pair: one arrive.expect_tx per CTA, both on the leader's barrier
       mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
-      mbar_init(&tmem_empty_bar[a], p.tma_epilogue ? kEpiThreads : 128);
+      mbar_init(&tmem_empty_bar[a], kPair ? 2 * kEpiThreads : (p.tma_epilogue ? kEpiThreads : 128));
     }
     mbar_init(res_full_bar, 1);
     mbar_init(res_empty_bar, kEpiThreads);
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_ptr_smem, 512);
-    tmem_relinquish();
+    if (kPair) { tmem_alloc_2sm(tmem_ptr_smem, 512); tmem_relinquish_2sm(); }
+    else { tmem_alloc(tmem_ptr_smem, 512); tmem_relinquish(); }
   }
   tc_fence_before();
   __syncthreads();
+  if (kPair) cluster_sync_all();   // the peer's barriers must be initialised before any remote arrive / multicast commit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -142,8 +157,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t tx_bytes = (uint32_t)stage_bytes;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(p, tile);
+      for (int work = work0; work < p.total_work; work += work_stride) {
+        const TileCoord t = decode_tile(p, work_to_tile(p, work, rank));
         for (int s = 0; s < p.nseg; ++s) {
           const int taps = p.seg_taps[s];
           for (int tap = 0; tap < taps; ++tap) {
@@ -153,9 +168,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
               mbar_wait(&empty_bar[stage], phase ^ 1);
               uint8_t* a_dst = smem + stage * stage_bytes;
               uint8_t* b_dst = a_dst + kABytes;
-              mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
-              tma_load_4d(a_dst, &p.mapA[s], &full_bar[stage], ch * kBlockK, t.x0 + dx, t.y0 + dy, t.n0);
-              tma_load_2d(b_dst, &p.mapB[s], &full_bar[stage], ch * kBlockK, tap * p.Cout_pad + t.nn0);
+              if (kPair) {
+                // this CTA's pixel tile + its half of the weight rows; completion is counted on the LEADER's barrier
+                const uint32_t fb = leader_addr(&full_bar[stage]);
+                mbar_arrive_expect_tx_cluster(fb, tx_bytes);
+                tma_load_4d_2sm(a_dst, &p.mapA[s], fb, ch * kBlockK, t.x0 + dx, t.y0 + dy, t.n0);
+                tma_load_2d_2sm(b_dst, &p.mapB[s], fb, ch * kBlockK, tap * p.Cout_pad + t.nn0 + rank * p.b_rows);
+              } else {
+                mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+                tma_load_4d(a_dst, &p.mapA[s], &full_bar[stage], ch * kBlockK, t.x0 + dx, t.y0 + dy, t.n0);
+                tma_load_2d(b_dst, &p.mapB[s], &full_bar[stage], ch * kBlockK, tap * p.Cout_pad + t.nn0);
+              }
               if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
             }
           }
@@ -164,12 +187,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (single thread) =====================
-    if (lane == 0) {
+    if (lane == 0 && rank == 0) {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int work = work0; work < p.total_work; work += work_stride) {
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
@@ -182,12 +205,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
             // advance 16 bf16 = 32 bytes inside the 128B swizzle atom: +2 in the (addr>>4) field
-            umma_bf16_ss(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), p.idesc, (kb | k) ? 1u : 0u);
+            if (kPair) umma_bf16_ss_2sm(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), p.idesc, (kb | k) ? 1u : 0u);
+            else umma_bf16_ss(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), p.idesc, (kb | k) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs retire
+          // frees the smem stage (in both CTAs of a pair) when these MMAs retire
+          if (kPair) umma_commit_2sm(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
           if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (of both CTAs)
+        if (kPair) umma_commit_2sm(&tmem_full_bar[acc]); else umma_commit(&tmem_full_bar[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -196,8 +222,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     if (lane == 0 && p.tma_epilogue && p.res_mode == 1) {
       const int n_slabs = p.BN / 64;
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(p, tile);
+      for (int work = work0; work < p.total_work; work += work_stride) {
+        const TileCoord t = decode_tile(p, work_to_tile(p, work, rank));
         for (int s0 = 0; s0 < n_slabs; s0 += 2, ++it) {
           const int ns = (n_slabs - s0) < 2 ? (n_slabs - s0) : 2;
           mbar_wait(res_empty_bar, (it & 1) ^ 1);
@@ -217,8 +243,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     const uint32_t swz = (uint32_t)(row & 7);
     int acc = 0;
     uint32_t acc_phase = 0, res_it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const TileCoord t = decode_tile(p, tile);
+    for (int work = work0; work < p.total_work; work += work_stride) {
+      const TileCoord t = decode_tile(p, work_to_tile(p, work, rank));
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
@@ -230,9 +256,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           tmem_ld_32x32(t_row + (uint32_t)((s0 + g) * 64 + 32), v1);
           tmem_ld_wait();
         }
-        if (s0 + 2 >= n_slabs) {   // last TMEM read of this tile: hand the accumulator back to the MMA warp
+        if (s0 + 2 >= n_slabs) {   // last TMEM read of this tile: hand the accumulator back to the (leader's) MMA warp
           tc_fence_before();
-          mbar_arrive(&tmem_empty_bar[acc]);
+          if (kPair) mbar_arrive_cluster(leader_addr(&tmem_empty_bar[acc]));
+          else mbar_arrive(&tmem_empty_bar[acc]);
         }
         // the staging tile (and bias_s) may be rewritten once the previous TMA store has finished reading it
         if (epi_tid == 0) tma_store_wait_read();
@@ -408,9 +435,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 
   tc_fence_before();
   __syncthreads();
+  if (kPair) cluster_sync_all();   // the peer may still be reading this CTA's operands / arriving on its barriers
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (kPair) tmem_dealloc_2sm(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -421,12 +449,20 @@ struct ConvPlan {
   size_t smem_bytes;
 };
 
-static int pick_bn(int cout_pad) {
-  if (cout_pad == 16 || cout_pad == 32 || cout_pad == 64 || cout_pad == 128 || cout_pad == 256) return cout_pad;
-  if (cout_pad % 256 == 0) return 256;
-  if (cout_pad % 128 == 0) return 128;
-  if (cout_pad % 64 == 0) return 64;
-  return -1;
+// N tile: the widest of {256, 128, 64} dividing Cout_pad that still yields about one work item per SM (deep 8x8 / 16x16
+// levels have few pixel tiles; narrower N tiles keep more SMs busy there); 16 / 32 for the tiny-Cout convs.
+static int pick_bn(int cout_pad, int m_tiles) {
+  if (cout_pad == 16 || cout_pad == 32) return cout_pad;
+  if (cout_pad % 64 != 0) return -1;
+  const int sms = num_sms();
+  int best = -1;
+  for (int bn : {256, 128, 64}) {
+    if (cout_pad % bn != 0) continue;
+    if (best < 0) best = bn;
+    if ((long)m_tiles * (cout_pad / bn) >= sms) return bn;
+    best = bn;   // not enough tiles yet: try narrower
+  }
+  return best;
 }
 
 int conv_plan_build(const kdip_conv_desc* d, ConvPlan* plan) {
@@ -435,8 +471,7 @@ int conv_plan_build(const kdip_conv_desc* d, ConvPlan* plan) {
   KDIP_REQUIRE(d->N > 0 && d->H > 0 && d->W > 0, KDIP_ESHAPE, "conv: bad geometry N=%d H=%d W=%d", d->N, d->H, d->W);
   ConvParams& p = plan->params;
   memset(&p, 0, sizeof(p));
-  const int BN = pick_bn(d->Cout_pad);
-  KDIP_REQUIRE(BN > 0, KDIP_ESHAPE, "conv: Cout_pad=%d unsupported (need 16, 32 or a multiple of 64)", d->Cout_pad);
+  int BN = 0;
   KDIP_REQUIRE(d->Cout >= 1 && d->Cout <= d->Cout_pad, KDIP_ESHAPE, "conv: Cout=%d > Cout_pad=%d", d->Cout, d->Cout_pad);
   KDIP_REQUIRE(d->out_mode == 1 || (d->Cout == d->Cout_pad && d->Cout % 32 == 0), KDIP_ESHAPE,
                "conv: bf16 NHWC output needs Cout == Cout_pad, multiple of 32 (got %d/%d)", d->Cout, d->Cout_pad);
@@ -456,13 +491,23 @@ int conv_plan_build(const kdip_conv_desc* d, ConvPlan* plan) {
   p.tiles_x = (d->W + p.TW - 1) / p.TW;
   p.tiles_y = (d->H + p.TH - 1) / p.TH;
   p.tiles_n = (d->N + p.TN - 1) / p.TN;
+  const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
+  BN = pick_bn(d->Cout_pad, m_tiles);
+  KDIP_REQUIRE(BN > 0, KDIP_ESHAPE, "conv: Cout_pad=%d unsupported (need 16, 32 or a multiple of 64)", d->Cout_pad);
   p.BN = BN;
   p.n_tiles = d->Cout_pad / BN;
   p.total_tiles = p.tiles_x * p.tiles_y * p.tiles_n * p.n_tiles;
   p.Cout_pad = d->Cout_pad;
   p.Cout = d->Cout;
   p.nseg = d->nseg;
-  p.idesc = umma_idesc_bf16(kBlockM, BN);
+  // TMA-store epilogue for bf16 NHWC outputs in 64-channel slabs without pooled / upsampled skips or fused statistics
+  p.tma_epilogue = (d->out_mode == 0 && BN >= 64 && d->Cout == d->Cout_pad && (d->res_mode == 0 || d->res_mode == 1) &&
+                    d->chan_stats == nullptr) ? 1 : 0;
+  // CTA pairs whenever the pixel tiles pair up
+  p.pair = (p.tma_epilogue && (m_tiles % 2 == 0)) ? 1 : 0;
+  p.b_rows = p.pair ? BN / 2 : BN;
+  p.total_work = p.pair ? (m_tiles / 2) * p.n_tiles : p.total_tiles;
+  p.idesc = umma_idesc_bf16(p.pair ? 2 * kBlockM : kBlockM, BN);
   p.bias = d->bias;
   p.residual = reinterpret_cast<const __nv_bfloat16*>(d->residual);
   p.res_mode = d->res_mode;
@@ -482,13 +527,10 @@ int conv_plan_build(const kdip_conv_desc* d, ConvPlan* plan) {
     int rc = encode_tmap_bf16_4d(&p.mapA[s], sg.act, (uint64_t)sg.C, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N, kBlockK,
                                  (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TN);
     if (rc != KDIP_OK) return rc;
-    rc = encode_tmap_bf16_2d(&p.mapB[s], sg.wgt, (uint64_t)sg.C, (uint64_t)sg.taps * d->Cout_pad, kBlockK, (uint32_t)BN);
+    rc = encode_tmap_bf16_2d(&p.mapB[s], sg.wgt, (uint64_t)sg.C, (uint64_t)sg.taps * d->Cout_pad, kBlockK, (uint32_t)p.b_rows);
     if (rc != KDIP_OK) return rc;
   }
 
-  // TMA-store epilogue for bf16 NHWC outputs in 64-channel slabs without pooled / upsampled skips or fused statistics
-  p.tma_epilogue = (d->out_mode == 0 && BN >= 64 && d->Cout == d->Cout_pad && (d->res_mode == 0 || d->res_mode == 1) &&
-                    d->chan_stats == nullptr) ? 1 : 0;
   int extra = 1024 /*bias + barriers*/;
   if (p.tma_epilogue) {
     extra += kStagingBytes + (d->res_mode == 1 ? kStagingBytes : 0);
@@ -502,7 +544,7 @@ int conv_plan_build(const kdip_conv_desc* d, ConvPlan* plan) {
       if (rc != KDIP_OK) return rc;
     }
   }
-  const int stage_bytes = kABytes + BN * 128;
+  const int stage_bytes = kABytes + p.b_rows * 128;
   const int budget = 227 * 1024 - extra - 1024 /*align slack*/ - 256;
   int stages = budget / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
@@ -510,17 +552,39 @@ int conv_plan_build(const kdip_conv_desc* d, ConvPlan* plan) {
   p.num_stages = stages;
   plan->smem_bytes = (size_t)stages * stage_bytes + 1024 /*align slack*/ + extra + 256;
   int sms = num_sms();
-  plan->grid = p.total_tiles < sms ? p.total_tiles : sms;
+  if (p.pair) {
+    const int clusters = sms / 2;
+    plan->grid = 2 * (p.total_work < clusters ? p.total_work : clusters);
+  } else {
+    plan->grid = p.total_tiles < sms ? p.total_tiles : sms;
+  }
   return KDIP_OK;
 }
 
 int conv_plan_launch(const ConvPlan* plan, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    KDIP_CUDA(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    KDIP_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    KDIP_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  conv_gemm_kernel<<<plan->grid, kThreads, plan->smem_bytes, stream>>>(plan->params);
+  if (plan->params.pair) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(plan->grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = plan->smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    KDIP_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<true>, plan->params));
+    count_launch();
+    return KDIP_OK;
+  }
+  conv_gemm_kernel<false><<<plan->grid, kThreads, plan->smem_bytes, stream>>>(plan->params);
   KDIP_LAUNCH_CHECK();
   return KDIP_OK;
 }
