@@ -16,8 +16,12 @@
 //   owning a 64-channel slab.  tcgen05.ld (2 x 32 columns in flight) -> +bias (shared memory) -> + identity residual (its
 //   tile is TMA-loaded by a dedicated producer thread, unet.py:257,306) -> bf16 -> 128B-swizzled staging tile in shared
 //   memory -> TMA store (cp.async.bulk.tensor, full 128 B lines; no scattered per-lane sectors).
+//   Optional fused GroupNorm statistics: per-(image, channel) sum / sum of squares of the stored tile, read back from the
+//   staging tile (conflict-free) and accumulated with 256 fp32 REDs per 128-channel pass.
 // Legacy epilogue (4 warps, per-lane global loads/stores) for the rare shapes: fp32 NCHW outputs with <= 32 channels (head,
-//   input gradient), 2x2 avg-pool / nearest-up skip paths (unet.py:190-197), fused channel statistics.
+//   input gradient), 2x2 avg-pool / nearest-up skip paths (unet.py:190-197).
+#include <stdlib.h>
+
 #include "kdip_common.cuh"
 
 namespace kdip {
@@ -38,6 +42,7 @@ struct ConvParams {
   CUtensorMap mapRes;   // identity residual, same geometry
   int tma_epilogue;     // 1: 8-warp TMA-store epilogue; 0: legacy 4-warp epilogue
   int pair;             // 1: CTA pairs (cta_group::2, M = 256 per pair, B split across the two CTAs)
+  int mt;               // pixel tiles per work item (1 or 2): mt = 2 shares every weight stage between two M=128 accumulators
   int b_rows;           // weight rows each CTA loads per k-block: BN (single) or BN/2 (pair)
   int total_work;       // persistent-loop trip count: tiles (single) or pair tiles (pair)
   int seg_taps[3];
@@ -52,6 +57,7 @@ struct ConvParams {
   const float* bias;
   const __nv_bfloat16* residual;
   int res_mode;
+  int res_tma;          // 1: the skip tile is TMA-loaded (res_mode 1; res_mode 3 with a half-size source box)
   void* out;
   int out_mode;
   float out_scale;
@@ -82,11 +88,12 @@ __device__ __forceinline__ void load8_bf16(const __nv_bfloat16* p, float (&f)[8]
   f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
 }
 
-// work item -> tile index of this CTA.  Pair mode: work = pm * n_tiles + nt covers M-tiles 2pm (leader) and 2pm+1 (peer).
-__device__ __forceinline__ int work_to_tile(const ConvParams& p, int work, int rank) {
-  if (!p.pair) return work;
+// work item -> tile index of this CTA's j-th pixel tile.  work = pm * n_tiles + nt.
+//   single CTA: M-tiles pm*mt + j;   pair mode (mt = 1): M-tiles 2pm (leader) and 2pm+1 (peer).
+__device__ __forceinline__ int work_to_tile(const ConvParams& p, int work, int rank, int j) {
   const int nt = work % p.n_tiles, pm = work / p.n_tiles;
-  return (2 * pm + rank) * p.n_tiles + nt;
+  const int m = p.pair ? (2 * pm + rank) : (pm * p.mt + j);
+  return m * p.n_tiles + nt;
 }
 
 template <bool kPair>
@@ -96,13 +103,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
 
-  const int stage_bytes = kABytes + p.b_rows * 128;
+  const int mt = p.mt;
+  const int a_bytes = mt * kABytes;
+  const int stage_bytes = a_bytes + p.b_rows * 128;
   const int rank = kPair ? (int)cluster_ctarank() : 0;
   const int work0 = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int work_stride = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   uint8_t* staging = smem + p.num_stages * stage_bytes;                       // [2][128 rows][128 B], TMA-store source
   uint8_t* res_stage = staging + (p.tma_epilogue ? kStagingBytes : 0);        // residual tile, same layout
-  uint8_t* after = res_stage + ((p.tma_epilogue && p.res_mode == 1) ? kStagingBytes : 0);
+  uint8_t* after = res_stage + (p.res_tma ? kStagingBytes : 0);
   float* bias_s = reinterpret_cast<float*>(after);                            // [256]
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(after + 1024);
   uint64_t* empty_bar = full_bar + kMaxStages;
@@ -122,7 +131,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     }
     if (p.tma_epilogue) {
       tma_prefetch_desc(&p.mapOut);
-      if (p.res_mode == 1) tma_prefetch_desc(&p.mapRes);
+      if (p.res_tma) tma_prefetch_desc(&p.mapRes);
     }
   }
   if (warp == 1 && lane == 0) {
@@ -158,7 +167,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       uint32_t phase = 0;
       const uint32_t tx_bytes = (uint32_t)stage_bytes;
       for (int work = work0; work < p.total_work; work += work_stride) {
-        const TileCoord t = decode_tile(p, work_to_tile(p, work, rank));
+        const TileCoord t = decode_tile(p, work_to_tile(p, work, rank, 0));
+        const TileCoord t1 = decode_tile(p, work_to_tile(p, work, rank, mt - 1));
         for (int s = 0; s < p.nseg; ++s) {
           const int taps = p.seg_taps[s];
           for (int tap = 0; tap < taps; ++tap) {
@@ -167,7 +177,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             for (int ch = 0; ch < p.seg_chunks[s]; ++ch) {
               mbar_wait(&empty_bar[stage], phase ^ 1);
               uint8_t* a_dst = smem + stage * stage_bytes;
-              uint8_t* b_dst = a_dst + kABytes;
+              uint8_t* b_dst = a_dst + a_bytes;
               if (kPair) {
                 // this CTA's pixel tile + its half of the weight rows; completion is counted on the LEADER's barrier
                 const uint32_t fb = leader_addr(&full_bar[stage]);
@@ -177,6 +187,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
               } else {
                 mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
                 tma_load_4d(a_dst, &p.mapA[s], &full_bar[stage], ch * kBlockK, t.x0 + dx, t.y0 + dy, t.n0);
+                if (mt == 2) tma_load_4d(a_dst + kABytes, &p.mapA[s], &full_bar[stage], ch * kBlockK, t1.x0 + dx, t1.y0 + dy, t1.n0);
                 tma_load_2d(b_dst, &p.mapB[s], &full_bar[stage], ch * kBlockK, tap * p.Cout_pad + t.nn0);
               }
               if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
@@ -195,18 +206,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       for (int work = work0; work < p.total_work; work += work_stride) {
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * mt * p.BN);
         for (int kb = 0; kb < kblocks_total; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
           const uint64_t a_desc = umma_desc_sw128(a_addr);
-          const uint64_t b_desc = umma_desc_sw128(a_addr + kABytes);
+          const uint64_t a1_desc = umma_desc_sw128(a_addr + kABytes);
+          const uint64_t b_desc = umma_desc_sw128(a_addr + a_bytes);
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
             // advance 16 bf16 = 32 bytes inside the 128B swizzle atom: +2 in the (addr>>4) field
             if (kPair) umma_bf16_ss_2sm(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), p.idesc, (kb | k) ? 1u : 0u);
-            else umma_bf16_ss(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), p.idesc, (kb | k) ? 1u : 0u);
+            else {
+              umma_bf16_ss(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), p.idesc, (kb | k) ? 1u : 0u);
+              if (mt == 2) umma_bf16_ss(d_tmem + (uint32_t)p.BN, a1_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), p.idesc, (kb | k) ? 1u : 0u);
+            }
           }
           // frees the smem stage (in both CTAs of a pair) when these MMAs retire
           if (kPair) umma_commit_2sm(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
@@ -219,17 +234,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     }
   } else if (warp == 3) {
     // ===================== residual producer: TMA-loads the identity-skip tile of every output tile =====================
-    if (lane == 0 && p.tma_epilogue && p.res_mode == 1) {
+    if (lane == 0 && p.res_tma) {
       const int n_slabs = p.BN / 64;
+      // nearest-up skip (unet.py:107,190-197): the 128-pixel output tile reads a (TH/2 x TW/2) box of the half-resolution source
+      const int up = p.res_mode == 3 ? 1 : 0;
+      const uint32_t slab_bytes = up ? kSlabBytes / 4 : kSlabBytes;
       uint32_t it = 0;
       for (int work = work0; work < p.total_work; work += work_stride) {
-        const TileCoord t = decode_tile(p, work_to_tile(p, work, rank));
-        for (int s0 = 0; s0 < n_slabs; s0 += 2, ++it) {
-          const int ns = (n_slabs - s0) < 2 ? (n_slabs - s0) : 2;
-          mbar_wait(res_empty_bar, (it & 1) ^ 1);
-          mbar_arrive_expect_tx(res_full_bar, (uint32_t)(ns * kSlabBytes));
-          for (int j = 0; j < ns; ++j)
-            tma_load_4d(res_stage + j * kSlabBytes, &p.mapRes, res_full_bar, t.nn0 + (s0 + j) * 64, t.x0, t.y0, t.n0);
+        for (int j = 0; j < mt; ++j) {
+          const TileCoord t = decode_tile(p, work_to_tile(p, work, rank, j));
+          for (int s0 = 0; s0 < n_slabs; s0 += 2, ++it) {
+            const int ns = (n_slabs - s0) < 2 ? (n_slabs - s0) : 2;
+            mbar_wait(res_empty_bar, (it & 1) ^ 1);
+            mbar_arrive_expect_tx(res_full_bar, (uint32_t)ns * slab_bytes);
+            for (int jj = 0; jj < ns; ++jj)
+              tma_load_4d(res_stage + jj * kSlabBytes, &p.mapRes, res_full_bar, t.nn0 + (s0 + jj) * 64, t.x0 >> up, t.y0 >> up, t.n0);
+          }
         }
       }
     }
@@ -241,13 +261,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     const int epi_tid = threadIdx.x - 128;
     const int n_slabs = p.BN / 64;
     const uint32_t swz = (uint32_t)(row & 7);
+    // row of this output pixel's skip value inside the TMA-loaded residual tile
+    int res_r = row;
+    if (p.res_mode == 3) {
+      const int tw = row % p.TW, th = (row / p.TW) % p.TH, tn = row / (p.TW * p.TH);
+      res_r = (tn * (p.TH >> 1) + (th >> 1)) * (p.TW >> 1) + (tw >> 1);
+    }
+    const uint32_t res_swz = (uint32_t)(res_r & 7);
     int acc = 0;
     uint32_t acc_phase = 0, res_it = 0;
     for (int work = work0; work < p.total_work; work += work_stride) {
-      const TileCoord t = decode_tile(p, work_to_tile(p, work, rank));
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
+     for (int mj = 0; mj < mt; ++mj) {
+      const TileCoord t = decode_tile(p, work_to_tile(p, work, rank, mj));
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * mt + mj) * p.BN);
       for (int s0 = 0; s0 < n_slabs; s0 += 2) {
         const bool active = (s0 + g) < n_slabs;
         uint32_t v0[32], v1[32];
@@ -256,7 +284,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           tmem_ld_32x32(t_row + (uint32_t)((s0 + g) * 64 + 32), v1);
           tmem_ld_wait();
         }
-        if (s0 + 2 >= n_slabs) {   // last TMEM read of this tile: hand the accumulator back to the (leader's) MMA warp
+        if (s0 + 2 >= n_slabs && mj == mt - 1) {   // last TMEM read of this work item: hand the accumulator back to the (leader's) MMA warp
           tc_fence_before();
           if (kPair) mbar_arrive_cluster(leader_addr(&tmem_empty_bar[acc]));
           else mbar_arrive(&tmem_empty_bar[acc]);
@@ -265,13 +293,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         if (epi_tid == 0) tma_store_wait_read();
         if (p.bias != nullptr && epi_tid < 128 && s0 * 64 + epi_tid < p.BN) bias_s[epi_tid] = __ldg(p.bias + t.nn0 + s0 * 64 + epi_tid);
         named_bar_sync(1, kEpiThreads);
-        if (p.res_mode == 1) {
+        if (p.res_tma) {
           mbar_wait(res_full_bar, res_it & 1);
           ++res_it;
         }
         if (active) {
           uint8_t* dst_row = staging + g * kSlabBytes + row * 128;
-          const uint8_t* res_row = res_stage + g * kSlabBytes + row * 128;
+          const uint8_t* res_row = res_stage + g * kSlabBytes + res_r * 128;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {     // 8 chunks of 8 channels (16 B)
             float f[8];
@@ -283,8 +311,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
               f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w; f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
             }
             const uint32_t off = ((uint32_t)j ^ swz) << 4;
-            if (p.res_mode == 1) {
-              const uint4 ru = *reinterpret_cast<const uint4*>(res_row + off);
+            if (p.res_tma) {
+              const uint4 ru = *reinterpret_cast<const uint4*>(res_row + (((uint32_t)j ^ res_swz) << 4));
               const float2 r0 = unpack_bf16(ru.x), r1 = unpack_bf16(ru.y), r2 = unpack_bf16(ru.z), r3 = unpack_bf16(ru.w);
               f[0] += r0.x; f[1] += r0.y; f[2] += r1.x; f[3] += r1.y; f[4] += r2.x; f[5] += r2.y; f[6] += r3.x; f[7] += r3.y;
             }
@@ -294,8 +322,41 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           }
           fence_proxy_async();   // make the staging writes visible to the TMA (async proxy)
         }
-        if (p.res_mode == 1) mbar_arrive(res_empty_bar);
+        if (p.res_tma) mbar_arrive(res_empty_bar);
         named_bar_sync(2, kEpiThreads);
+        if (p.chan_stats != nullptr) {
+          // Per-(image, channel) sum / sum of squares of the STORED bf16 values for the next GroupNorm (nn.py:17-19), read back
+          // from the staged tile.  Warp (gs, oct) owns 8 channel pairs of slab gs; lane = rq*8 + pair, rq picks rows
+          // 2rq + 8i + {0,1}: the four row classes of one LDS hit four distinct swizzle chunk pairs -> conflict-free.
+          const int wi = warp - 4, gs = wi >> 2, oct = wi & 3;
+          if (s0 + gs < n_slabs) {
+            const int j = oct * 8 + (lane & 7), rq = lane >> 3;
+            const uint8_t* sbase = staging + gs * kSlabBytes + (j & 3) * 4;
+            const int ipi = 16 / p.TN;   // 8-row groups per image
+            const int ch = t.nn0 + (s0 + gs) * 64 + 2 * j;
+            for (int img = 0; img < p.TN; ++img) {
+              float a0 = 0.f, a1 = 0.f, q0 = 0.f, q1 = 0.f;
+              for (int i = img * ipi; i < (img + 1) * ipi; ++i) {
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                  const int r = 2 * rq + 8 * i + b;
+                  const uint32_t wv = *reinterpret_cast<const uint32_t*>(sbase + r * 128 + ((((uint32_t)j >> 2) ^ (uint32_t)(r & 7)) << 4));
+                  const float2 v = unpack_bf16(wv);
+                  a0 += v.x; a1 += v.y; q0 = fmaf(v.x, v.x, q0); q1 = fmaf(v.y, v.y, q1);
+                }
+              }
+#pragma unroll
+              for (int o = 8; o <= 16; o <<= 1) {
+                a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+                q0 += __shfl_xor_sync(0xffffffffu, q0, o); q1 += __shfl_xor_sync(0xffffffffu, q1, o);
+              }
+              if (lane < 8 && t.n0 + img < p.N) {
+                float* st = p.chan_stats + ((size_t)(t.n0 + img) * p.Cout + ch) * 2;
+                atomicAdd(st, a0); atomicAdd(st + 1, q0); atomicAdd(st + 2, a1); atomicAdd(st + 3, q1);
+              }
+            }
+          }
+        }
         if (epi_tid == 0) {
           const int ns = (n_slabs - s0) < 2 ? (n_slabs - s0) : 2;
           for (int j = 0; j < ns; ++j)
@@ -303,6 +364,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           tma_store_commit();
         }
       }
+     }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (epi_tid == 0) tma_store_wait_all();
@@ -465,6 +527,31 @@ static int pick_bn(int cout_pad, int m_tiles) {
   return best;
 }
 
+static void set_smem_attr() {
+  static bool attr_set = false;
+  if (attr_set) return;
+  cudaFuncSetAttribute(conv_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaFuncSetAttribute(conv_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  attr_set = true;
+}
+
+static int max_active_pairs(size_t smem_bytes) {
+  set_smem_attr();
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(2 * num_sms());
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, conv_gemm_kernel<true>, &cfg) != cudaSuccess) { cudaGetLastError(); return -1; }
+  return n;
+}
+
 int conv_plan_build(const kdip_conv_desc* d, ConvPlan* plan) {
   KDIP_REQUIRE(d != nullptr && plan != nullptr, KDIP_EINVAL, "conv: null descriptor");
   KDIP_REQUIRE(d->nseg >= 1 && d->nseg <= 3, KDIP_EINVAL, "conv: nseg must be 1..3 (got %d)", d->nseg);
@@ -501,12 +588,35 @@ int conv_plan_build(const kdip_conv_desc* d, ConvPlan* plan) {
   p.Cout = d->Cout;
   p.nseg = d->nseg;
   // TMA-store epilogue for bf16 NHWC outputs in 64-channel slabs without pooled / upsampled skips or fused statistics
-  p.tma_epilogue = (d->out_mode == 0 && BN >= 64 && d->Cout == d->Cout_pad && (d->res_mode == 0 || d->res_mode == 1) &&
-                    d->chan_stats == nullptr) ? 1 : 0;
+  // (fused statistics read whole staged tiles: only when the pixel tiles divide the image)
+  const bool whole_tiles = (d->W % p.TW == 0) && (d->H % p.TH == 0);
+  // nearest-up skips ride the TMA path when every tile maps to a whole half-resolution box
+  const bool up_ok = d->res_mode == 3 && whole_tiles && p.TW % 2 == 0 && p.TH % 2 == 0;
+  p.tma_epilogue = (d->out_mode == 0 && BN >= 64 && d->Cout == d->Cout_pad && (d->res_mode == 0 || d->res_mode == 1 || up_ok) &&
+                    (d->chan_stats == nullptr || whole_tiles)) ? 1 : 0;
+  p.res_tma = (p.tma_epilogue && d->res_mode != 0) ? 1 : 0;
   // CTA pairs whenever the pixel tiles pair up
   p.pair = (p.tma_epilogue && (m_tiles % 2 == 0)) ? 1 : 0;
+  // tuning switches for A/B measurements (tools/time_unet.py): KDIP_CONV_PAIR=0, KDIP_CONV_TMAEPI=0
+  if (const char* e = getenv("KDIP_CONV_TMAEPI")) { if (atoi(e) == 0) { p.tma_epilogue = 0; p.pair = 0; p.res_tma = 0; } }
+  if (const char* e = getenv("KDIP_CONV_PAIR")) { if (atoi(e) == 0) p.pair = 0; }
+  // Two pixel tiles per work item when the N tile is narrow: the SM's L2 read port (~64 B/clk) feeds M128 x N128 x K64 MMAs
+  // (256 clk) with 32 KB per k-block = 128 B/clk, i.e. at most half rate; sharing the weight stage between two accumulators
+  // needs 48 KB per 512 clk.  TMEM: 2 buffers x 2 tiles x BN columns <= 512.  Only when the wave quantisation stays benign.
+  p.mt = 1;
+  if (p.tma_epilogue && BN <= 128 && m_tiles % 2 == 0) {
+    const int sms = num_sms();
+    const long w1 = (long)m_tiles * p.n_tiles, w2 = w1 / 2;
+    const double e1 = (double)w1 / (double)(((w1 + sms - 1) / sms) * sms), e2 = (double)w2 / (double)(((w2 + sms - 1) / sms) * sms);
+    if (w2 >= sms && e2 >= e1 - 0.08) p.mt = 2;
+  }
+  if (const char* e = getenv("KDIP_CONV_MT")) {   // 1: never; 2: whenever legal (tests force it on small shapes)
+    if (atoi(e) == 1) p.mt = 1;
+    if (atoi(e) == 2 && p.tma_epilogue && BN <= 128 && m_tiles % 2 == 0) p.mt = 2;
+  }
+  if (p.mt == 2) p.pair = 0;
   p.b_rows = p.pair ? BN / 2 : BN;
-  p.total_work = p.pair ? (m_tiles / 2) * p.n_tiles : p.total_tiles;
+  p.total_work = p.pair ? (m_tiles / 2) * p.n_tiles : (m_tiles / p.mt) * p.n_tiles;
   p.idesc = umma_idesc_bf16(p.pair ? 2 * kBlockM : kBlockM, BN);
   p.bias = d->bias;
   p.residual = reinterpret_cast<const __nv_bfloat16*>(d->residual);
@@ -533,41 +643,44 @@ int conv_plan_build(const kdip_conv_desc* d, ConvPlan* plan) {
 
   int extra = 1024 /*bias + barriers*/;
   if (p.tma_epilogue) {
-    extra += kStagingBytes + (d->res_mode == 1 ? kStagingBytes : 0);
+    extra += kStagingBytes + (p.res_tma ? kStagingBytes : 0);
     int rc = encode_tmap_bf16_4d(&p.mapOut, d->out, (uint64_t)d->Cout, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N, 64,
                                  (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TN);
     if (rc != KDIP_OK) return rc;
-    if (d->res_mode == 1) {
+    if (p.res_tma) {
       KDIP_REQUIRE(((uintptr_t)d->residual % 16) == 0, KDIP_EALIGN, "conv: residual must be 16B aligned");
-      rc = encode_tmap_bf16_4d(&p.mapRes, d->residual, (uint64_t)d->Cout, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N, 64,
-                               (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TN);
+      const int sh = d->res_mode == 3 ? 1 : 0;
+      rc = encode_tmap_bf16_4d(&p.mapRes, d->residual, (uint64_t)d->Cout, (uint64_t)(d->W >> sh), (uint64_t)(d->H >> sh), (uint64_t)d->N, 64,
+                               (uint32_t)(p.TW >> sh), (uint32_t)(p.TH >> sh), (uint32_t)p.TN);
       if (rc != KDIP_OK) return rc;
     }
   }
-  const int stage_bytes = kABytes + p.b_rows * 128;
+  const int stage_bytes = p.mt * kABytes + p.b_rows * 128;
   const int budget = 227 * 1024 - extra - 1024 /*align slack*/ - 256;
   int stages = budget / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
+  if (const char* e = getenv("KDIP_CONV_STAGES")) { const int v = atoi(e); if (v >= 2 && v < stages) stages = v; }
   KDIP_REQUIRE(stages >= 2, KDIP_ESHAPE, "conv: not enough shared memory for a 2-stage pipeline (BN=%d)", BN);
   p.num_stages = stages;
   plan->smem_bytes = (size_t)stages * stage_bytes + 1024 /*align slack*/ + extra + 256;
+  if (getenv("KDIP_CONV_DEBUG"))
+    fprintf(stderr, "[kdip conv] N=%d H=%d W=%d Cout=%d K=%d taps=%d nseg=%d BN=%d stages=%d pair=%d mt=%d tmaepi=%d res=%d work=%d smem=%zu\n", d->N, d->H,
+            d->W, d->Cout, d->seg[0].C, d->seg[0].taps, d->nseg, BN, stages, p.pair, p.mt, p.tma_epilogue, d->res_mode, p.total_work, plan->smem_bytes);
   int sms = num_sms();
   if (p.pair) {
-    const int clusters = sms / 2;
+    // a persistent kernel must be fully co-resident: ask the driver how many CTA pairs fit at this shared-memory size
+    int clusters = max_active_pairs(plan->smem_bytes);
+    if (clusters <= 0 || clusters > sms / 2) clusters = sms / 2;
+    if (getenv("KDIP_CONV_DEBUG")) fprintf(stderr, "[kdip conv] pair clusters co-resident: %d\n", clusters);
     plan->grid = 2 * (p.total_work < clusters ? p.total_work : clusters);
   } else {
-    plan->grid = p.total_tiles < sms ? p.total_tiles : sms;
+    plan->grid = p.total_work < sms ? p.total_work : sms;
   }
   return KDIP_OK;
 }
 
 int conv_plan_launch(const ConvPlan* plan, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    KDIP_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    KDIP_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
+  set_smem_attr();
   if (plan->params.pair) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));

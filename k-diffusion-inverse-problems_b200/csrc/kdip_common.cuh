@@ -141,11 +141,13 @@ __device__ __forceinline__ void cluster_sync_all() {
 }
 // shared-window address of the same object in the pair's leader (even-rank) CTA: clear the peer bit (CUTLASS Sm100MmaPeerBitMask)
 __device__ __forceinline__ uint32_t leader_addr(const void* p) { return smem_u32(p) & 0xFEFFFFFFu; }
+// Default semantics (.release.cta, as CUTLASS's ClusterTransactionBarrier does): an explicit .release.cluster makes ptxas emit
+// MEMBAR.ALL.GPU + ERRBAR in front of every arrive, which serialises the single-thread TMA producer (2.7x slower main loop).
 __device__ __forceinline__ void mbar_arrive_expect_tx_cluster(uint32_t addr, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(addr), "r"(bytes) : "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(addr), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(addr) : "memory");
 }
 // TMA loads issued by either CTA of a pair; the transaction bytes are reported to the barrier at `bar_addr` (leader's)
 __device__ __forceinline__ void tma_load_2d_2sm(void* dst, const void* map, uint32_t bar_addr, int c0, int c1) {

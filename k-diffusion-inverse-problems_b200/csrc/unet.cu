@@ -14,6 +14,8 @@
 // torch.cat (unet.py:662) never materialises: consumers read the two sources.
 // The VJP (autograd sites condition/condition.py:136,146,155,172,269; parameters never need gradients) walks the same
 // plan backwards with dgrad convs (same kernel, flipped weights) and a 3-kernel GroupNorm backward.
+#include <stdlib.h>
+
 #include <functional>
 #include <map>
 #include <string>
@@ -509,8 +511,11 @@ static int build_launch_plan(kdip_unet* u, int N, void* ws, size_t ws_bytes, siz
       ops.push_back(o);
     }
   };
+  // GroupNorm statistics of every block output ride in the producing conv's epilogue (kdip_conv_desc.chan_stats);
+  // KDIP_UNFUSED_STATS=1 restores the separate chan_stats pass (A/B measurements)
+  const bool fused_stats = getenv("KDIP_UNFUSED_STATS") == nullptr;
   auto stats_op = [&](std::vector<Op>& ops, const Act& t) {
-    if (!emit) return;
+    if (!emit || fused_stats) return;
     const bf16* p = t.p; float* st = t.stats; int P = t.H * t.W, C = t.C, n = N;
     ops.push_back([=](cudaStream_t s) { return launch_chan_stats(p, n, P, C, st, s); });
   };
@@ -560,6 +565,7 @@ static int build_launch_plan(kdip_unet* u, int N, void* ws, size_t ws_bytes, siz
         d0.N = N; d0.H = H; d0.W = H; d0.Cout_pad = b.cout; d0.Cout = b.cout; d0.nseg = 1;
         d0.seg[0].act = scrB; d0.seg[0].C = 64; d0.seg[0].wgt = u->w_in_i2c; d0.seg[0].taps = 1;
         d0.bias = u->b_in; d0.out = h.p; d0.out_mode = 0; d0.out_scale = 1.f;
+        if (fused_stats) d0.chan_stats = h.stats;
         add_conv_op(F, conv(d0));
       }
       stats_op(F, h);
@@ -580,6 +586,8 @@ static int build_launch_plan(kdip_unet* u, int N, void* ws, size_t ws_bytes, siz
       sr.mr1 = (float*)B.alloc((size_t)N * 32 * 2 * 4);
       sr.ab2 = (float*)B.alloc((size_t)N * b.cout * 2 * 4);
       sr.mr2 = (float*)B.alloc((size_t)N * 32 * 2 * 4);
+      // Downsample blocks: the pooled identity skip avg_pool2d(x) is a by-product of the GroupNorm-apply pass
+      bf16* xpool = (b.updown == 1 && b.cin == b.cout) ? (bf16*)B.alloc((size_t)N * H * H * b.cout * 2) : nullptr;
       sr.h1 = B.new_act(H, H, b.cout);
       sr.h1.stats = take_stats(b.cout);
       sr.out = B.new_act(H, H, b.cout);
@@ -592,12 +600,13 @@ static int build_launch_plan(kdip_unet* u, int N, void* ws, size_t ws_bytes, siz
         F.push_back([=](cudaStream_t s) {
           return launch_gn_finalize(s0.stats, s0.C, s1.stats, s1.C, n, P_in, w.g1, w.b1, nullptr, 0, 0, ab1, mr1, s);
         });
-        F.push_back([=](cudaStream_t s) { return launch_gn_apply(s0.p, s0.C, s1.p, s1.C, n, Hin, Hin, ab1, 1, rs, scrA, s); });
+        F.push_back([=](cudaStream_t s) { return launch_gn_apply(s0.p, s0.C, s1.p, s1.C, n, Hin, Hin, ab1, 1, rs, scrA, s, xpool); });
         kdip_conv_desc d1;
         memset(&d1, 0, sizeof(d1));
         d1.N = N; d1.H = Ho; d1.W = Ho; d1.Cout_pad = cout; d1.Cout = cout; d1.nseg = 1;
         d1.seg[0].act = scrA; d1.seg[0].C = cin; d1.seg[0].wgt = w.w1; d1.seg[0].taps = 9;
         d1.bias = w.bias1; d1.out = h1.p; d1.out_mode = 0; d1.out_scale = 1.f;
+        if (fused_stats) d1.chan_stats = h1.stats;
         add_conv_op(F, conv(d1));
         stats_op(F, h1);
         F.push_back([=](cudaStream_t s) {
@@ -614,10 +623,11 @@ static int build_launch_plan(kdip_unet* u, int N, void* ws, size_t ws_bytes, siz
           d2.nseg = 2;
           if (s1.C > 0) { d2.seg[2].act = s1.p; d2.seg[2].C = s1.C; d2.seg[2].wgt = w.ws1; d2.seg[2].taps = 1; d2.nseg = 3; }
         } else {
-          d2.residual = s0.p;
-          d2.res_mode = b.updown == 1 ? 2 : (b.updown == 2 ? 3 : 1);
+          d2.residual = xpool ? (const void*)xpool : (const void*)s0.p;
+          d2.res_mode = b.updown == 1 ? (xpool ? 1 : 2) : (b.updown == 2 ? 3 : 1);
         }
         d2.bias = w.bias2; d2.out = sr.out.p; d2.out_mode = 0; d2.out_scale = 1.f;
+        if (fused_stats) d2.chan_stats = sr.out.stats;
         add_conv_op(F, conv(d2));
       }
       stats_op(F, sr.out);
@@ -654,6 +664,7 @@ static int build_launch_plan(kdip_unet* u, int N, void* ws, size_t ws_bytes, siz
         dp.N = N; dp.H = H; dp.W = H; dp.Cout_pad = c; dp.Cout = c; dp.nseg = 1;
         dp.seg[0].act = att.p; dp.seg[0].C = c; dp.seg[0].wgt = w.wproj; dp.seg[0].taps = 1;
         dp.bias = w.bproj; dp.residual = x.p; dp.res_mode = 1; dp.out = sa.out.p; dp.out_mode = 0; dp.out_scale = 1.f;
+        if (fused_stats) dp.chan_stats = sa.out.stats;
         add_conv_op(F, conv(dp));
       }
       stats_op(F, sa.out);

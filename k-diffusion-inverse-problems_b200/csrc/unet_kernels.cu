@@ -207,7 +207,7 @@ static constexpr int GN_UNROLL = 4;
 template <int RS, bool SILU>
 __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const bf16* __restrict__ s0, int C0, const bf16* __restrict__ s1, int C1,
                                                               int H, int W, const float* __restrict__ ab, bf16* __restrict__ out,
-                                                              int pix_per_block) {
+                                                              int pix_per_block, bf16* __restrict__ pool_out) {
   const int C = C0 + C1, vec = C >> 3;
   const int rows = GN_THREADS / vec;
   const int cv = threadIdx.x % vec, row = threadIdx.x / vec;
@@ -249,6 +249,13 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const bf16* __rest
 #pragma unroll
       for (int j = 0; j < 8; ++j) r[j] = 0.25f * ((r0[j] + r1[j]) + (r2[j] + r3[j]));
       stv(dst + (size_t)p * C, pack8(r));
+      if (pool_out != nullptr) {
+        // the identity skip of a Downsample ResBlock, x_upd(x) = avg_pool2d(x) (unet.py:136,190-197), from the same loads
+        unpack8(v0, r0); unpack8(v1, r1); unpack8(v2, r2); unpack8(v3, r3);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = 0.25f * ((r0[j] + r1[j]) + (r2[j] + r3[j]));
+        stv(pool_out + ((size_t)n * Ho * Wo + p) * C + c0, pack8(r));
+      }
     }
   } else {
     for (; p < p_end; p += rows) {
@@ -274,7 +281,7 @@ static inline void gn_grid(int N, int P, int rows, dim3* grid, int* pix_per_bloc
 }
 
 int launch_gn_apply(const bf16* src0, int C0, const bf16* src1, int C1, int N, int H, int W, const float* ab, int act_silu,
-                    int resample, bf16* out, cudaStream_t s) {
+                    int resample, bf16* out, cudaStream_t s, bf16* pool_out) {
   const int C = C0 + C1;
   KDIP_REQUIRE(C0 % 8 == 0 && C1 % 8 == 0 && C / 8 <= GN_THREADS && C > 0, KDIP_ESHAPE, "gn_apply: channels %d+%d unsupported", C0, C1);
   KDIP_REQUIRE(resample != RS_AVGPOOL2 || (H % 2 == 0 && W % 2 == 0), KDIP_ESHAPE, "gn_apply: avg-pool needs even H, W");
@@ -283,7 +290,8 @@ int launch_gn_apply(const bf16* src0, int C0, const bf16* src1, int C1, int N, i
   dim3 grid;
   int ppb;
   gn_grid(N, Pit, rows, &grid, &ppb);
-#define GN_APPLY(RS, SL) gn_apply_kernel<RS, SL><<<grid, GN_THREADS, 0, s>>>(src0, C0, src1, C1, H, W, ab, out, ppb)
+  KDIP_REQUIRE(pool_out == nullptr || resample == RS_AVGPOOL2, KDIP_EINVAL, "gn_apply: pool_out only with the avg-pool resample");
+#define GN_APPLY(RS, SL) gn_apply_kernel<RS, SL><<<grid, GN_THREADS, 0, s>>>(src0, C0, src1, C1, H, W, ab, out, ppb, pool_out)
   if (resample == RS_NONE) { if (act_silu) GN_APPLY(RS_NONE, true); else GN_APPLY(RS_NONE, false); }
   else if (resample == RS_AVGPOOL2) { if (act_silu) GN_APPLY(RS_AVGPOOL2, true); else GN_APPLY(RS_AVGPOOL2, false); }
   else { if (act_silu) GN_APPLY(RS_NEAREST_UP2, true); else GN_APPLY(RS_NEAREST_UP2, false); }
@@ -295,97 +303,180 @@ int launch_gn_apply(const bf16* src0, int C0, const bf16* src1, int C1, int N, i
 // ---------------------------------------------------------------------------------------------------------------------
 // GroupNorm backward
 // ---------------------------------------------------------------------------------------------------------------------
-// g_u at input pixel p = (y, x) of image n for this thread's 8 channels: resample^T(g_y) * act'(A*x + B)
-template <int RS, bool SILU>
-__device__ __forceinline__ void grad_u8(const uint4& xraw, const float (&A)[8], const float (&B)[8], const bf16* __restrict__ gyb,
-                                        int y, int x, int H, int W, int C, float (&xf)[8], float (&g)[8]) {
-  unpack8(xraw, xf);
-  if (RS == RS_NONE) {
-    unpack8(ldv(gyb + ((size_t)y * W + x) * C), g);
-  } else if (RS == RS_AVGPOOL2) {
-    unpack8(ldv(gyb + ((size_t)(y >> 1) * (W >> 1) + (x >> 1)) * C), g);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) g[j] *= 0.25f;
+// Same channel-stationary scheme.  VEC = channels per thread: 4 (8-byte loads) whenever C/4 <= 256 threads - the per-channel
+// coefficient registers (A, B, k1, k2) and the two accumulators halve, so 4 CTAs of 256 threads fit per SM (<= 64 registers)
+// instead of 2 - else 8.  Every unroll batch issues ALL its loads (x, g_y incl. the 2x2 replicas, extra) before any math.
+template <int VEC>
+struct Raw {
+  uint32_t w[VEC / 2];
+};
+template <int VEC>
+__device__ __forceinline__ Raw<VEC> ldraw(const bf16* p) {
+  Raw<VEC> r;
+  if constexpr (VEC == 8) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+    r.w[0] = u.x; r.w[1] = u.y; r.w[2] = u.z; r.w[3] = u.w;
   } else {
-    const bf16* q = gyb + ((size_t)(2 * y) * (2 * W) + 2 * x) * C;
-    float a[8], b[8], c[8], d[8];
-    unpack8(ldv(q), a); unpack8(ldv(q + C), b); unpack8(ldv(q + (size_t)2 * W * C), c); unpack8(ldv(q + (size_t)(2 * W + 1) * C), d);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) g[j] = (a[j] + b[j]) + (c[j] + d[j]);
+    const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+    r.w[0] = u.x; r.w[1] = u.y;
   }
-  if (SILU) {
+  return r;
+}
+template <int VEC>
+__device__ __forceinline__ void unpackv(const Raw<VEC>& r, float (&f)[VEC]) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) g[j] *= dsilu_fast(fmaf(A[j], xf[j], B[j]));
+  for (int j = 0; j < VEC / 2; ++j) {
+    const float2 a = unpack_bf16(r.w[j]);
+    f[2 * j] = a.x; f[2 * j + 1] = a.y;
+  }
+}
+template <int VEC>
+__device__ __forceinline__ void storev(bf16* p, const float (&f)[VEC]) {
+  if constexpr (VEC == 8) {
+    uint4 u;
+    u.x = pack_bf16(f[0], f[1]); u.y = pack_bf16(f[2], f[3]); u.z = pack_bf16(f[4], f[5]); u.w = pack_bf16(f[6], f[7]);
+    *reinterpret_cast<uint4*>(p) = u;
+  } else {
+    uint2 u;
+    u.x = pack_bf16(f[0], f[1]); u.y = pack_bf16(f[2], f[3]);
+    *reinterpret_cast<uint2*>(p) = u;
+  }
+}
+// the g_y-resolution taps feeding input pixel (y, x): 1 (same / pooled resolution) or the 2x2 replicas of nearest-up
+template <int VEC, int RS>
+struct GTaps {
+  Raw<VEC> t[RS == RS_NEAREST_UP2 ? 4 : 1];
+};
+template <int VEC, int RS>
+__device__ __forceinline__ GTaps<VEC, RS> ld_gtaps(const bf16* __restrict__ gb, int y, int x, int W, int C) {
+  GTaps<VEC, RS> g;
+  if (RS == RS_NONE) {
+    g.t[0] = ldraw<VEC>(gb + ((size_t)y * W + x) * C);
+  } else if (RS == RS_AVGPOOL2) {
+    g.t[0] = ldraw<VEC>(gb + ((size_t)(y >> 1) * (W >> 1) + (x >> 1)) * C);
+  } else {
+    const bf16* q = gb + ((size_t)(2 * y) * (2 * W) + 2 * x) * C;
+    g.t[0] = ldraw<VEC>(q);
+    g.t[RS == RS_NEAREST_UP2 ? 1 : 0] = ldraw<VEC>(q + C);
+    g.t[RS == RS_NEAREST_UP2 ? 2 : 0] = ldraw<VEC>(q + (size_t)2 * W * C);
+    g.t[RS == RS_NEAREST_UP2 ? 3 : 0] = ldraw<VEC>(q + (size_t)(2 * W + 1) * C);
+  }
+  return g;
+}
+// resample^T applied to the taps
+template <int VEC, int RS>
+__device__ __forceinline__ void sum_gtaps(const GTaps<VEC, RS>& g, float (&r)[VEC]) {
+  unpackv<VEC>(g.t[0], r);
+  if (RS == RS_AVGPOOL2) {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) r[j] *= 0.25f;
+  } else if (RS == RS_NEAREST_UP2) {
+    float b[VEC], c[VEC], d[VEC];
+    unpackv<VEC>(g.t[RS == RS_NEAREST_UP2 ? 1 : 0], b);
+    unpackv<VEC>(g.t[RS == RS_NEAREST_UP2 ? 2 : 0], c);
+    unpackv<VEC>(g.t[RS == RS_NEAREST_UP2 ? 3 : 0], d);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) r[j] = (r[j] + b[j]) + (c[j] + d[j]);
+  }
+}
+// (A, B) of VEC consecutive channels
+template <int VEC>
+__device__ __forceinline__ void load_abv(const float* __restrict__ ab, int n, int C, int c0, float (&A)[VEC], float (&B)[VEC]) {
+  const float4* q = reinterpret_cast<const float4*>(ab + ((size_t)n * C + c0) * 2);
+#pragma unroll
+  for (int j = 0; j < VEC / 2; ++j) {
+    const float4 t = __ldg(q + j);
+    A[2 * j] = t.x; B[2 * j] = t.y; A[2 * j + 1] = t.z; B[2 * j + 1] = t.w;
   }
 }
 
-template <int RS, bool SILU>
-__global__ void __launch_bounds__(GN_THREADS) gn_bwd_reduce_kernel(const bf16* __restrict__ s0, int C0, const bf16* __restrict__ s1,
-                                                                   int C1, int H, int W, const float* __restrict__ ab,
-                                                                   const bf16* __restrict__ gy, int pix_per_block,
-                                                                   float* __restrict__ red_out) {
-  extern __shared__ float red[];   // [rows][vec*16]
-  const int C = C0 + C1, vec = C >> 3;
+template <int RS>
+struct BwdUnroll {
+  static constexpr int value = RS == RS_NEAREST_UP2 ? 2 : 4;
+};
+
+template <int VEC, int RS, bool SILU>
+__global__ void __launch_bounds__(GN_THREADS, VEC == 4 ? 4 : 2)
+    gn_bwd_reduce_kernel(const bf16* __restrict__ s0, int C0, const bf16* __restrict__ s1, int C1, int H, int W,
+                         const float* __restrict__ ab, const bf16* __restrict__ gy, int pix_per_block, float* __restrict__ red_out) {
+  extern __shared__ float red[];   // [rows][vec*2*VEC]
+  constexpr int U = BwdUnroll<RS>::value;
+  const int C = C0 + C1, vec = C / VEC;
   const int rows = GN_THREADS / vec;
   const int cv = threadIdx.x % vec, row = threadIdx.x / vec;
-  const int n = blockIdx.y, c0 = cv * 8, P = H * W;
-  float r1[8], r2[8];
+  const int n = blockIdx.y, c0 = cv * VEC, P = H * W;
+  float r1[VEC], r2[VEC];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) r1[j] = r2[j] = 0.f;
+  for (int j = 0; j < VEC; ++j) r1[j] = r2[j] = 0.f;
   if (row < rows) {
-    float A[8], B[8];
-    load_ab(ab, n, C, c0, A, B);
-    const ChanView in = chan_view(s0, C0, s1, C1, n, P, c0);
+    float A[VEC], B[VEC];
+    load_abv<VEC>(ab, n, C, c0, A, B);
+    const bf16* xb;
+    int xs;
+    if (c0 < C0) { xb = s0 + (size_t)n * P * C0 + c0; xs = C0; } else { xb = s1 + (size_t)n * P * C1 + (c0 - C0); xs = C1; }
     const int Pg = RS == RS_AVGPOOL2 ? P / 4 : (RS == RS_NEAREST_UP2 ? P * 4 : P);
     const bf16* gyb = gy + (size_t)n * Pg * C + c0;
     const int p_end = min(P, (int)(blockIdx.x + 1) * pix_per_block);
     int p = blockIdx.x * pix_per_block + row;
-    for (; p + (GN_UNROLL - 1) * rows < p_end; p += GN_UNROLL * rows) {
-      uint4 v[GN_UNROLL];
+    auto accum = [&](const Raw<VEC>& xr, const GTaps<VEC, RS>& gt) {
+      float xf[VEC], g[VEC];
+      unpackv<VEC>(xr, xf);
+      sum_gtaps<VEC, RS>(gt, g);
 #pragma unroll
-      for (int k = 0; k < GN_UNROLL; ++k) v[k] = ldv(in.base + (size_t)(p + k * rows) * in.stride);
-#pragma unroll
-      for (int k = 0; k < GN_UNROLL; ++k) {
-        const int pp = p + k * rows, y = pp / W, x = pp - y * W;
-        float xf[8], g[8];
-        grad_u8<RS, SILU>(v[k], A, B, gyb, y, x, H, W, C, xf, g);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { r1[j] += g[j]; r2[j] = fmaf(g[j], xf[j], r2[j]); }
+      for (int j = 0; j < VEC; ++j) {
+        const float gu = SILU ? g[j] * dsilu_fast(fmaf(A[j], xf[j], B[j])) : g[j];
+        r1[j] += gu;
+        r2[j] = fmaf(gu, xf[j], r2[j]);
       }
+    };
+    for (; p + (U - 1) * rows < p_end; p += U * rows) {
+      Raw<VEC> xr[U];
+      GTaps<VEC, RS> gt[U];
+#pragma unroll
+      for (int k = 0; k < U; ++k) xr[k] = ldraw<VEC>(xb + (size_t)(p + k * rows) * xs);
+#pragma unroll
+      for (int k = 0; k < U; ++k) {
+        const int pp = p + k * rows, y = pp / W, x = pp - y * W;
+        gt[k] = ld_gtaps<VEC, RS>(gyb, y, x, W, C);
+      }
+#pragma unroll
+      for (int k = 0; k < U; ++k) accum(xr[k], gt[k]);
     }
     for (; p < p_end; p += rows) {
       const int y = p / W, x = p - y * W;
-      float xf[8], g[8];
-      grad_u8<RS, SILU>(ldv(in.base + (size_t)p * in.stride), A, B, gyb, y, x, H, W, C, xf, g);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { r1[j] += g[j]; r2[j] = fmaf(g[j], xf[j], r2[j]); }
+      accum(ldraw<VEC>(xb + (size_t)p * xs), ld_gtaps<VEC, RS>(gyb, y, x, W, C));
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { red[(row * vec + cv) * 16 + j] = r1[j]; red[(row * vec + cv) * 16 + 8 + j] = r2[j]; }
+    for (int j = 0; j < VEC; ++j) { red[(row * vec + cv) * 2 * VEC + j] = r1[j]; red[(row * vec + cv) * 2 * VEC + VEC + j] = r2[j]; }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < vec * 16; i += blockDim.x) {
+  for (int i = threadIdx.x; i < vec * 2 * VEC; i += blockDim.x) {
     float acc = 0.f;
-    for (int r = 0; r < rows; ++r) acc += red[r * vec * 16 + i];
-    const int c = (i >> 4) * 8 + (i & 7);
-    const int which = (i >> 3) & 1;
+    for (int r = 0; r < rows; ++r) acc += red[r * vec * 2 * VEC + i];
+    const int c = (i / (2 * VEC)) * VEC + (i % VEC);
+    const int which = (i / VEC) & 1;
     atomicAdd(red_out + ((size_t)n * C + c) * 2 + which, acc);
   }
 }
+
+static inline int bwd_vec(int C) { return (C % 4 == 0 && C / 4 <= GN_THREADS) ? 4 : 8; }
 
 int launch_gn_bwd_reduce(const bf16* src0, int C0, const bf16* src1, int C1, int N, int H, int W, const float* ab, int act_silu,
                          int resample, const bf16* gy, float* red, cudaStream_t s) {
   const int C = C0 + C1;
   KDIP_REQUIRE(C0 % 8 == 0 && C1 % 8 == 0 && C / 8 <= GN_THREADS && C > 0, KDIP_ESHAPE, "gn_bwd_reduce: channels %d+%d unsupported", C0, C1);
-  const int vec = C / 8, rows = GN_THREADS / vec;
+  const int VEC = bwd_vec(C);
+  const int vec = C / VEC, rows = GN_THREADS / vec;
   dim3 grid;
   int ppb;
   gn_grid(N, H * W, rows, &grid, &ppb);
-  const size_t smem = (size_t)rows * vec * 16 * sizeof(float);
-#define GN_RED(RS, SL) gn_bwd_reduce_kernel<RS, SL><<<grid, GN_THREADS, smem, s>>>(src0, C0, src1, C1, H, W, ab, gy, ppb, red)
-  if (resample == RS_NONE) { if (act_silu) GN_RED(RS_NONE, true); else GN_RED(RS_NONE, false); }
-  else if (resample == RS_AVGPOOL2) { if (act_silu) GN_RED(RS_AVGPOOL2, true); else GN_RED(RS_AVGPOOL2, false); }
-  else { if (act_silu) GN_RED(RS_NEAREST_UP2, true); else GN_RED(RS_NEAREST_UP2, false); }
+  const size_t smem = (size_t)rows * vec * 2 * VEC * sizeof(float);
+#define GN_RED(V, RS, SL) gn_bwd_reduce_kernel<V, RS, SL><<<grid, GN_THREADS, smem, s>>>(src0, C0, src1, C1, H, W, ab, gy, ppb, red)
+#define GN_RED_V(RS, SL) do { if (VEC == 4) GN_RED(4, RS, SL); else GN_RED(8, RS, SL); } while (0)
+  if (resample == RS_NONE) { if (act_silu) GN_RED_V(RS_NONE, true); else GN_RED_V(RS_NONE, false); }
+  else if (resample == RS_AVGPOOL2) { if (act_silu) GN_RED_V(RS_AVGPOOL2, true); else GN_RED_V(RS_AVGPOOL2, false); }
+  else { if (act_silu) GN_RED_V(RS_NEAREST_UP2, true); else GN_RED_V(RS_NEAREST_UP2, false); }
+#undef GN_RED_V
 #undef GN_RED
   KDIP_LAUNCH_CHECK();
   return KDIP_OK;
@@ -430,28 +521,30 @@ int launch_gn_bwd_finalize(const float* red, const float* ab, const float* mr, c
 }
 
 // g_x = k0*g_u + k1 + k2*x (+ extra), written per source (the concat's two gradients go to two tensors)
-template <int RS, bool SILU, int EXTRA>
-__global__ void __launch_bounds__(GN_THREADS) gn_bwd_apply_kernel(const bf16* __restrict__ s0, int C0, const bf16* __restrict__ s1,
-                                                                  int C1, int H, int W, const float* __restrict__ ab,
-                                                                  const float* __restrict__ k, const bf16* __restrict__ gy,
-                                                                  const bf16* __restrict__ extra, int pix_per_block,
-                                                                  bf16* __restrict__ d0, bf16* __restrict__ d1) {
-  const int C = C0 + C1, vec = C >> 3;
+template <int VEC, int RS, bool SILU, int EXTRA>
+__global__ void __launch_bounds__(GN_THREADS, VEC == 4 ? 4 : 2)
+    gn_bwd_apply_kernel(const bf16* __restrict__ s0, int C0, const bf16* __restrict__ s1, int C1, int H, int W,
+                        const float* __restrict__ ab, const float* __restrict__ k, const bf16* __restrict__ gy,
+                        const bf16* __restrict__ extra, int pix_per_block, bf16* __restrict__ d0, bf16* __restrict__ d1) {
+  constexpr int U = (RS == RS_NEAREST_UP2 && EXTRA == 2) ? 1 : BwdUnroll<RS>::value;
+  const int C = C0 + C1, vec = C / VEC;
   const int rows = GN_THREADS / vec;
   const int cv = threadIdx.x % vec, row = threadIdx.x / vec;
   if (row >= rows) return;
-  const int n = blockIdx.y, c0 = cv * 8, P = H * W;
-  float A[8], B[8], K1[8], K2[8];
-  load_ab(ab, n, C, c0, A, B);
+  const int n = blockIdx.y, c0 = cv * VEC, P = H * W;
+  float A[VEC], B[VEC], K1[VEC], K2[VEC];
+  load_abv<VEC>(ab, n, C, c0, A, B);
   {
     const float4* kq = reinterpret_cast<const float4*>(k + ((size_t)n * C + c0) * 4);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < VEC; ++j) {
       const float4 kk = __ldg(kq + j);
       K1[j] = kk.y; K2[j] = kk.z;       // kk.x == A[j]
     }
   }
-  const ChanView in = chan_view(s0, C0, s1, C1, n, P, c0);
+  const bf16* xb;
+  int xs;
+  if (c0 < C0) { xb = s0 + (size_t)n * P * C0 + c0; xs = C0; } else { xb = s1 + (size_t)n * P * C1 + (c0 - C0); xs = C1; }
   const int Pg = RS == RS_AVGPOOL2 ? P / 4 : (RS == RS_NEAREST_UP2 ? P * 4 : P);
   const bf16* gyb = gy + (size_t)n * Pg * C + c0;
   const bf16* exb = nullptr;
@@ -461,33 +554,51 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_apply_kernel(const bf16* __
   const int Cd = (c0 < C0) ? C0 : C1;
   const int p_end = min(P, (int)(blockIdx.x + 1) * pix_per_block);
   int p = blockIdx.x * pix_per_block + row;
-  auto body = [&](const uint4& xraw, int pp) {
-    const int y = pp / W, x = pp - y * W;
-    float xf[8], g[8], r[8];
-    grad_u8<RS, SILU>(xraw, A, B, gyb, y, x, H, W, C, xf, g);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) r[j] = fmaf(A[j], g[j], fmaf(K2[j], xf[j], K1[j]));
-    if (EXTRA == 1) {
-      float e[8];
-      unpack8(ldv(exb + (size_t)pp * C), e);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) r[j] += e[j];
-    } else if (EXTRA == 2) {
-      float e[8], dummy[8];
-      grad_u8<RS, false>(xraw, A, B, exb, y, x, H, W, C, dummy, e);     // plain resample^T, no activation factor
-#pragma unroll
-      for (int j = 0; j < 8; ++j) r[j] += e[j];
-    }
-    stv(dst + (size_t)pp * Cd, pack8(r));
+  struct Loaded {
+    Raw<VEC> x;
+    GTaps<VEC, RS> g;
+    Raw<VEC> e1;                 // EXTRA == 1
+    GTaps<VEC, RS> e2;           // EXTRA == 2
   };
-  for (; p + (GN_UNROLL - 1) * rows < p_end; p += GN_UNROLL * rows) {
-    uint4 v[GN_UNROLL];
+  auto load = [&](int pp) {
+    Loaded L;
+    const int y = pp / W, x = pp - y * W;
+    L.x = ldraw<VEC>(xb + (size_t)pp * xs);
+    L.g = ld_gtaps<VEC, RS>(gyb, y, x, W, C);
+    if (EXTRA == 1) L.e1 = ldraw<VEC>(exb + (size_t)pp * C);
+    if (EXTRA == 2) L.e2 = ld_gtaps<VEC, RS>(exb, y, x, W, C);
+    return L;
+  };
+  auto finish = [&](const Loaded& L, int pp) {
+    float xf[VEC], g[VEC], r[VEC];
+    unpackv<VEC>(L.x, xf);
+    sum_gtaps<VEC, RS>(L.g, g);
 #pragma unroll
-    for (int kk = 0; kk < GN_UNROLL; ++kk) v[kk] = ldv(in.base + (size_t)(p + kk * rows) * in.stride);
+    for (int j = 0; j < VEC; ++j) {
+      const float gu = SILU ? g[j] * dsilu_fast(fmaf(A[j], xf[j], B[j])) : g[j];
+      r[j] = fmaf(A[j], gu, fmaf(K2[j], xf[j], K1[j]));
+    }
+    if (EXTRA == 1) {
+      float e[VEC];
+      unpackv<VEC>(L.e1, e);
 #pragma unroll
-    for (int kk = 0; kk < GN_UNROLL; ++kk) body(v[kk], p + kk * rows);
+      for (int j = 0; j < VEC; ++j) r[j] += e[j];
+    } else if (EXTRA == 2) {
+      float e[VEC];
+      sum_gtaps<VEC, RS>(L.e2, e);     // plain resample^T, no activation factor
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) r[j] += e[j];
+    }
+    storev<VEC>(dst + (size_t)pp * Cd, r);
+  };
+  for (; p + (U - 1) * rows < p_end; p += U * rows) {
+    Loaded L[U];
+#pragma unroll
+    for (int kk = 0; kk < U; ++kk) L[kk] = load(p + kk * rows);
+#pragma unroll
+    for (int kk = 0; kk < U; ++kk) finish(L[kk], p + kk * rows);
   }
-  for (; p < p_end; p += rows) body(ldv(in.base + (size_t)p * in.stride), p);
+  for (; p < p_end; p += rows) finish(load(p), p);
 }
 
 int launch_gn_bwd_apply(const bf16* src0, int C0, const bf16* src1, int C1, int N, int H, int W, const float* ab,
@@ -497,16 +608,19 @@ int launch_gn_bwd_apply(const bf16* src0, int C0, const bf16* src1, int C1, int 
   KDIP_REQUIRE(C0 % 8 == 0 && C1 % 8 == 0 && C / 8 <= GN_THREADS && C > 0, KDIP_ESHAPE, "gn_bwd_apply: channels %d+%d unsupported", C0, C1);
   KDIP_REQUIRE(extra_mode == 0 || extra != nullptr, KDIP_EINVAL, "gn_bwd_apply: extra_mode set without tensor");
   KDIP_REQUIRE(extra_mode >= 0 && extra_mode <= 2, KDIP_EINVAL, "gn_bwd_apply: bad extra_mode %d", extra_mode);
-  const int rows = GN_THREADS / (C / 8);
+  const int VEC = bwd_vec(C);
+  const int rows = GN_THREADS / (C / VEC);
   dim3 grid;
   int ppb;
   gn_grid(N, H * W, rows, &grid, &ppb);
-#define GN_BA(RS, SL, EX) gn_bwd_apply_kernel<RS, SL, EX><<<grid, GN_THREADS, 0, s>>>(src0, C0, src1, C1, H, W, ab, k, gy, extra, ppb, dst0, dst1)
-#define GN_BA_EX(RS, SL) do { if (extra_mode == 0) GN_BA(RS, SL, 0); else if (extra_mode == 1) GN_BA(RS, SL, 1); else GN_BA(RS, SL, 2); } while (0)
+#define GN_BA(V, RS, SL, EX) gn_bwd_apply_kernel<V, RS, SL, EX><<<grid, GN_THREADS, 0, s>>>(src0, C0, src1, C1, H, W, ab, k, gy, extra, ppb, dst0, dst1)
+#define GN_BA_V(RS, SL, EX) do { if (VEC == 4) GN_BA(4, RS, SL, EX); else GN_BA(8, RS, SL, EX); } while (0)
+#define GN_BA_EX(RS, SL) do { if (extra_mode == 0) GN_BA_V(RS, SL, 0); else if (extra_mode == 1) GN_BA_V(RS, SL, 1); else GN_BA_V(RS, SL, 2); } while (0)
   if (resample == RS_NONE) { if (act_silu) GN_BA_EX(RS_NONE, true); else GN_BA_EX(RS_NONE, false); }
   else if (resample == RS_AVGPOOL2) { if (act_silu) GN_BA_EX(RS_AVGPOOL2, true); else GN_BA_EX(RS_AVGPOOL2, false); }
   else { if (act_silu) GN_BA_EX(RS_NEAREST_UP2, true); else GN_BA_EX(RS_NEAREST_UP2, false); }
 #undef GN_BA_EX
+#undef GN_BA_V
 #undef GN_BA
   KDIP_LAUNCH_CHECK();
   return KDIP_OK;

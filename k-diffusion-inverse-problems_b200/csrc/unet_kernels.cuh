@@ -21,8 +21,9 @@ int launch_gn_finalize(const float* stats0, int C0, const float* stats1, int C1,
                        const float* beta, const float* film, int film_stride, int film_off, float* ab, float* mr, cudaStream_t s);
 
 // y = resample(act(A*x + B)) ; sources src0 [N,H,W,C0], src1 [N,H,W,C1] (or NULL), out [N,H',W',C0+C1]
+// pool_out (RS_AVGPOOL2 only, optional): also writes avg_pool2d(x) of the raw input [N,H/2,W/2,C] (the Downsample skip path)
 int launch_gn_apply(const bf16* src0, int C0, const bf16* src1, int C1, int N, int H, int W, const float* ab, int act_silu,
-                    int resample, bf16* out, cudaStream_t s);
+                    int resample, bf16* out, cudaStream_t s, bf16* pool_out = nullptr);
 
 // backward, pass 1: red[N][C][2] += (sum_p g_u, sum_p g_u*x) with g_u = resample^T(g_y) * act'(A*x+B)
 int launch_gn_bwd_reduce(const bf16* src0, int C0, const bf16* src1, int C1, int N, int H, int W, const float* ab, int act_silu,

@@ -93,6 +93,61 @@ def test_conv_residual_modes(mode):
     assert e < TOL
 
 
+@pytest.mark.parametrize("case", [(3, 8, 8, 128), (2, 32, 32, 256), (1, 64, 64, 64)], ids=lambda c: "x".join(map(str, c)))
+@pytest.mark.parametrize("variant", ["default", "mt2", "nopair"])
+def test_conv_nearest_up_skip_tma(case, variant, monkeypatch):
+    """Upsample ResBlock skip (unet.py:107,190-197): half-resolution source box TMA-loaded per output tile, in every tile mode."""
+    from gpu_util import pack_weight, run_conv, to_nchw_f32, to_nhwc_bf16, relerr
+    if variant == "mt2":
+        monkeypatch.setenv("KDIP_CONV_MT", "2")
+    if variant == "nopair":
+        monkeypatch.setenv("KDIP_CONV_PAIR", "0")
+        monkeypatch.setenv("KDIP_CONV_MT", "1")
+    N, H, W, C = case
+    x = _mk(N, C, H, W, 1)
+    w = _mk(C, C, 3, 3, 2) / (C * 9) ** 0.5
+    r = _mk(N, C, H // 2, W // 2, 5)
+    b = _mk(1, C, 1, 1, 3).flatten()
+    stats = torch.zeros(N, C, 2, device="cuda")
+    out = run_conv([(to_nhwc_bf16(x), pack_weight(w)[0], 9)], N, H, W, C, bias=b, residual=to_nhwc_bf16(r), res_mode=3, stats=stats)
+    ref = F.conv2d(_bf(x), _bf(w), b, padding=1) + F.interpolate(_bf(r), scale_factor=2, mode="nearest")
+    got = to_nchw_f32(out)
+    e = relerr(got, ref)
+    print(f"nearest-up skip {case} {variant}: rel err {e:.3e}")
+    assert e < TOL
+    assert torch.allclose(stats[..., 0], got.sum((2, 3)), rtol=1e-3, atol=2e-2)
+
+
+@pytest.mark.parametrize("case", [
+    (2, 16, 16, 64, 64, 9, 0),      # 4 pixel tiles -> 2 work items of 2 tiles
+    (4, 32, 32, 128, 128, 9, 1),    # identity residual, both tiles of a work item
+    (3, 8, 8, 128, 128, 9, 0),      # TN=2, odd N: 2 pixel tiles, the second one half out of range
+    (2, 32, 32, 192, 64, 1, 1),     # 1x1
+    (2, 16, 16, 64, 256, 9, 0),     # Cout 256 -> N tile 128 or 64 with several N tiles per pixel-tile pair
+], ids=lambda c: "x".join(map(str, c)))
+def test_conv_two_tiles_per_work_item(case, monkeypatch):
+    """mt = 2: two M=128 accumulators share every weight stage (forced on small shapes through KDIP_CONV_MT=2)."""
+    from gpu_util import pack_weight, run_conv, to_nchw_f32, to_nhwc_bf16, relerr
+    monkeypatch.setenv("KDIP_CONV_MT", "2")
+    N, H, W, Ci, Co, taps, res = case
+    k = 3 if taps == 9 else 1
+    x = _mk(N, Ci, H, W, 1)
+    w = _mk(Co, Ci, k, k, 2) / (Ci * taps) ** 0.5
+    b = _mk(1, Co, 1, 1, 3).flatten()
+    r = _mk(N, Co, H, W, 5) if res else None
+    stats = torch.zeros(N, Co, 2, device="cuda")
+    out = run_conv([(to_nhwc_bf16(x), pack_weight(w)[0], taps)], N, H, W, Co, bias=b,
+                   residual=to_nhwc_bf16(r) if res else None, res_mode=res, stats=stats)
+    ref = F.conv2d(_bf(x), _bf(w), b, padding=k // 2) + (_bf(r) if res else 0)
+    got = to_nchw_f32(out)
+    assert torch.isfinite(got).all()
+    e = relerr(got, ref)
+    print(f"mt=2 conv {case}: rel err {e:.3e}")
+    assert e < TOL
+    assert torch.allclose(stats[..., 0], got.sum((2, 3)), rtol=1e-3, atol=2e-2)
+    assert torch.allclose(stats[..., 1], (got * got).sum((2, 3)), rtol=1e-3, atol=2e-2)
+
+
 def test_conv_three_segments():
     """conv3x3(a2) + 1x1 skip over two concatenated sources accumulated in one TMEM tile (unet.py:222,257,662)."""
     from gpu_util import pack_weight, run_conv, to_nchw_f32, to_nhwc_bf16, relerr
@@ -128,17 +183,31 @@ def test_conv_small_cout_fp32_nchw(cout):
     assert e < 1e-4          # fp32 store: only accumulation order differs
 
 
-def test_conv_chan_stats():
+@pytest.mark.parametrize("case", [
+    (3, 8, 8, 64, 64, 0),       # TN=2: one tile spans two images, odd N -> out-of-range image in the last tile
+    (2, 32, 32, 128, 128, 0),   # CTA pairs, two 64-channel slabs
+    (4, 16, 16, 64, 256, 1),    # BN=256: two staging passes; identity residual
+    (1, 64, 64, 64, 192, 0),    # 3 slabs: the second pass is half empty
+    (2, 16, 16, 64, 128, 2),    # avg-pool skip -> legacy epilogue statistics
+], ids=lambda c: "x".join(map(str, c)))
+def test_conv_chan_stats(case):
+    """GroupNorm statistics (nn.py:17-19) fused into the conv epilogue = sums over the stored bf16 output."""
     from gpu_util import pack_weight, run_conv, to_nchw_f32, to_nhwc_bf16
-    N, H, W, C = 3, 8, 8, 64   # TN=2 path: rows of a warp span two images
-    x = _mk(N, C, H, W, 1)
-    w = _mk(C, C, 3, 3, 2) / (C * 9) ** 0.5
+    N, H, W, Ci, C, res_mode = case
+    x = _mk(N, Ci, H, W, 1)
+    w = _mk(C, Ci, 3, 3, 2) / (Ci * 9) ** 0.5
     stats = torch.zeros(N, C, 2, device="cuda")
-    out = run_conv([(to_nhwc_bf16(x), pack_weight(w)[0], 9)], N, H, W, C, stats=stats)
+    res = None
+    if res_mode == 1:
+        res = to_nhwc_bf16(_mk(N, C, H, W, 5))
+    elif res_mode == 2:
+        res = to_nhwc_bf16(_mk(N, C, 2 * H, 2 * W, 5))
+    out = run_conv([(to_nhwc_bf16(x), pack_weight(w)[0], 9)], N, H, W, C, residual=res, res_mode=res_mode, stats=stats)
     got = to_nchw_f32(out)
+    assert torch.isfinite(got).all()
     s1, s2 = got.sum((2, 3)), (got * got).sum((2, 3))
-    assert torch.allclose(stats[..., 0], s1, rtol=1e-3, atol=1e-2)
-    assert torch.allclose(stats[..., 1], s2, rtol=1e-3, atol=1e-2)
+    assert torch.allclose(stats[..., 0], s1, rtol=1e-3, atol=2e-2), (stats[..., 0] - s1).abs().max()
+    assert torch.allclose(stats[..., 1], s2, rtol=1e-3, atol=2e-2), (stats[..., 1] - s2).abs().max()
 
 
 def test_conv_rejects_bad_shapes():

@@ -78,6 +78,29 @@ def test_groupnorm_forward_backward(C0, C1, rs, silu, film):
     print(f"gn bwd: rel err {e:.3e}")
     assert e < TOL
 
+    # extra_mode 2: the extra gradient lives at g_y's resolution and goes through resample^T only (identity-skip path of an
+    # up/down ResBlock, unet.py:190-197,257)
+    extra2 = _mk(N, C, Ho, Wo, seed=8)
+    z = xin.detach().clone().requires_grad_()
+    (ge,) = torch.autograd.grad(_resample(z, rs), z, _bf(extra2))
+    xin2 = xin.detach().clone().requires_grad_()
+    u2 = F.group_norm(xin2, 32, gamma, beta, eps=1e-5)
+    if film:
+        u2 = u2 * (1 + sc) + sh
+    y2 = _resample(F.silu(u2) if silu else u2, rs)
+    (gx2,) = torch.autograd.grad(y2, xin2, _bf(gy))
+    gx2 = gx2 + ge
+    extra2_n = to_nhwc_bf16(extra2)
+    red.zero_()
+    check(lib.kdip_layer_gn_bwd(ptr(s0), C0, ptr(s1), C1, N, H, W, ptr(ab), ptr(mr), silu, rs, ptr(gy_n),
+                                ptr(extra2_n), 2, ptr(red), ptr(kk), ptr(d0), ptr(d1) if C1 else None, st))
+    got = to_nchw_f32(d0)
+    if C1:
+        got = torch.cat([got, to_nchw_f32(d1)[:, :C1]], 1)
+    e = relerr(got, gx2)
+    print(f"gn bwd (extra at g_y resolution): rel err {e:.3e}")
+    assert e < TOL
+
 
 @pytest.mark.parametrize("T,heads,N", [(64, 1, 2), (256, 3, 2), (1024, 2, 1)])
 def test_attention_forward_backward(T, heads, N):
