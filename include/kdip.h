@@ -199,6 +199,17 @@ typedef struct {
   int out_mode;
   float out_scale;      /* multiplies the final value (out_mode 1 only; e.g. c_in for the input-VJP) */
   float* chan_stats;    /* optional fp32 [N,Cout,2] (sum, sum of squares) accumulated atomically; NULL to skip */
+  /* Optional fused GroupNorm-backward reduction (autograd of nn.py:17-19 + SiLU; condition/condition.py:136,146,155,172,269).
+   * The conv output g is the gradient wrt the normalised activation act(A x + B) of the tensor x = concat(gn_x0, gn_x1)
+   * (bf16 NHWC at the output resolution, gn_C0 + C1 = Cout, both multiples of 64):
+   *   gn_red[n][c][0] += sum_p g_u,  gn_red[n][c][1] += sum_p g_u x,  g_u = g act'(A x + B)   (g as stored, i.e. bf16-rounded)
+   * Needs bf16 NHWC output, no residual, Cout a multiple of 64 and image sides that are multiples of the pixel tile. */
+  const void* gn_x0;
+  const void* gn_x1;    /* or NULL */
+  int gn_C0;
+  int gn_silu;          /* 1: act = SiLU, 0: identity */
+  const float* gn_ab;   /* fp32 [N,Cout,2] folded affine (A, B) of the forward pass */
+  float* gn_red;        /* fp32 [N,Cout,2], zeroed by the caller; NULL to skip */
 } kdip_conv_desc;
 
 typedef struct kdip_conv_plan kdip_conv_plan; /* encoded TMA descriptors + launch geometry */

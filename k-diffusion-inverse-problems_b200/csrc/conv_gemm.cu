@@ -39,7 +39,8 @@ struct ConvParams {
   CUtensorMap mapA[3];
   CUtensorMap mapB[3];
   CUtensorMap mapOut;   // bf16 NHWC output, box {64, TW, TH, TN} (TMA-store epilogue)
-  CUtensorMap mapRes;   // identity residual, same geometry
+  CUtensorMap mapRes;   // identity residual, same geometry; or the first GroupNorm source of the fused backward reduction
+  CUtensorMap mapRes2;  // second (concatenated) GroupNorm source
   int tma_epilogue;     // 1: 8-warp TMA-store epilogue; 0: legacy 4-warp epilogue
   int pair;             // 1: CTA pairs (cta_group::2, M = 256 per pair, B split across the two CTAs)
   int mt;               // pixel tiles per work item (1 or 2): mt = 2 shares every weight stage between two M=128 accumulators
@@ -62,6 +63,10 @@ struct ConvParams {
   int out_mode;
   float out_scale;
   float* chan_stats;
+  // fused GroupNorm-backward reduction (kdip_conv_desc.gn_*): the x tile is TMA-loaded like a residual tile
+  const float* gn_ab;
+  float* gn_red;
+  int gn_C0, gn_silu, gn_two;
 };
 
 struct TileCoord {
@@ -89,10 +94,10 @@ __device__ __forceinline__ void load8_bf16(const __nv_bfloat16* p, float (&f)[8]
 }
 
 // work item -> tile index of this CTA's j-th pixel tile.  work = pm * n_tiles + nt.
-//   single CTA: M-tiles pm*mt + j;   pair mode (mt = 1): M-tiles 2pm (leader) and 2pm+1 (peer).
+//   single CTA: M-tiles pm*mt + j;   pair mode: the leader owns M-tiles 2pm*mt + j, the peer (2pm+1)*mt + j.
 __device__ __forceinline__ int work_to_tile(const ConvParams& p, int work, int rank, int j) {
   const int nt = work % p.n_tiles, pm = work / p.n_tiles;
-  const int m = p.pair ? (2 * pm + rank) : (pm * p.mt + j);
+  const int m = (p.pair ? (2 * pm + rank) : pm) * p.mt + j;
   return m * p.n_tiles + nt;
 }
 
@@ -132,6 +137,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     if (p.tma_epilogue) {
       tma_prefetch_desc(&p.mapOut);
       if (p.res_tma) tma_prefetch_desc(&p.mapRes);
+      if (p.gn_two) tma_prefetch_desc(&p.mapRes2);
     }
   }
   if (warp == 1 && lane == 0) {
@@ -183,6 +189,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                 const uint32_t fb = leader_addr(&full_bar[stage]);
                 mbar_arrive_expect_tx_cluster(fb, tx_bytes);
                 tma_load_4d_2sm(a_dst, &p.mapA[s], fb, ch * kBlockK, t.x0 + dx, t.y0 + dy, t.n0);
+                if (mt == 2) tma_load_4d_2sm(a_dst + kABytes, &p.mapA[s], fb, ch * kBlockK, t1.x0 + dx, t1.y0 + dy, t1.n0);
                 tma_load_2d_2sm(b_dst, &p.mapB[s], fb, ch * kBlockK, tap * p.Cout_pad + t.nn0 + rank * p.b_rows);
               } else {
                 mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
@@ -217,8 +224,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
             // advance 16 bf16 = 32 bytes inside the 128B swizzle atom: +2 in the (addr>>4) field
-            if (kPair) umma_bf16_ss_2sm(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), p.idesc, (kb | k) ? 1u : 0u);
-            else {
+            if (kPair) {
+              umma_bf16_ss_2sm(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), p.idesc, (kb | k) ? 1u : 0u);
+              if (mt == 2) umma_bf16_ss_2sm(d_tmem + (uint32_t)p.BN, a1_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), p.idesc, (kb | k) ? 1u : 0u);
+            } else {
               umma_bf16_ss(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), p.idesc, (kb | k) ? 1u : 0u);
               if (mt == 2) umma_bf16_ss(d_tmem + (uint32_t)p.BN, a1_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), p.idesc, (kb | k) ? 1u : 0u);
             }
@@ -247,8 +256,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             const int ns = (n_slabs - s0) < 2 ? (n_slabs - s0) : 2;
             mbar_wait(res_empty_bar, (it & 1) ^ 1);
             mbar_arrive_expect_tx(res_full_bar, (uint32_t)ns * slab_bytes);
-            for (int jj = 0; jj < ns; ++jj)
-              tma_load_4d(res_stage + jj * kSlabBytes, &p.mapRes, res_full_bar, t.nn0 + (s0 + jj) * 64, t.x0 >> up, t.y0 >> up, t.n0);
+            for (int jj = 0; jj < ns; ++jj) {
+              int c_off = t.nn0 + (s0 + jj) * 64;
+              const CUtensorMap* mp = &p.mapRes;
+              if (p.gn_red != nullptr && c_off >= p.gn_C0) { c_off -= p.gn_C0; mp = &p.mapRes2; }
+              tma_load_4d(res_stage + jj * kSlabBytes, mp, res_full_bar, c_off, t.x0 >> up, t.y0 >> up, t.n0);
+            }
           }
         }
       }
@@ -311,7 +324,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
               f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w; f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
             }
             const uint32_t off = ((uint32_t)j ^ swz) << 4;
-            if (p.res_tma) {
+            if (p.res_tma && p.gn_red == nullptr) {
               const uint4 ru = *reinterpret_cast<const uint4*>(res_row + (((uint32_t)j ^ res_swz) << 4));
               const float2 r0 = unpack_bf16(ru.x), r1 = unpack_bf16(ru.y), r2 = unpack_bf16(ru.z), r3 = unpack_bf16(ru.w);
               f[0] += r0.x; f[1] += r0.y; f[2] += r1.x; f[3] += r1.y; f[4] += r2.x; f[5] += r2.y; f[6] += r3.x; f[7] += r3.y;
@@ -322,8 +335,51 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           }
           fence_proxy_async();   // make the staging writes visible to the TMA (async proxy)
         }
-        if (p.res_tma) mbar_arrive(res_empty_bar);
+        if (p.res_tma && p.gn_red == nullptr) mbar_arrive(res_empty_bar);
         named_bar_sync(2, kEpiThreads);
+        if (p.gn_red != nullptr) {
+          // GroupNorm backward, pass 1, on the staged gradient tile g and the TMA-loaded x tile (same swizzled layout):
+          // red[n][c] += (sum g_u, sum g_u x), g_u = g act'(A x + B).  Same conflict-free column mapping as the statistics below.
+          const int wi = warp - 4, gs = wi >> 2, oct = wi & 3;
+          if (s0 + gs < n_slabs) {
+            const int j = oct * 8 + (lane & 7), rq = lane >> 3;
+            const uint8_t* gbase = staging + gs * kSlabBytes + (j & 3) * 4;
+            const uint8_t* xbase = res_stage + gs * kSlabBytes + (j & 3) * 4;
+            const int ipi = 16 / p.TN;
+            const int ch = t.nn0 + (s0 + gs) * 64 + 2 * j;
+            for (int img = 0; img < p.TN; ++img) {
+              const int n = t.n0 + img;
+              const float4 abv = __ldg(reinterpret_cast<const float4*>(p.gn_ab + ((size_t)(n < p.N ? n : p.N - 1) * p.Cout + ch) * 2));
+              float r10 = 0.f, r11 = 0.f, r20 = 0.f, r21 = 0.f;
+              for (int i = img * ipi; i < (img + 1) * ipi; ++i) {
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                  const int r = 2 * rq + 8 * i + b;
+                  const uint32_t off = (uint32_t)(r * 128) + ((((uint32_t)j >> 2) ^ (uint32_t)(r & 7)) << 4);
+                  const float2 g = unpack_bf16(*reinterpret_cast<const uint32_t*>(gbase + off));
+                  const float2 x = unpack_bf16(*reinterpret_cast<const uint32_t*>(xbase + off));
+                  float g0 = g.x, g1 = g.y;
+                  if (p.gn_silu) {
+                    g0 *= dsilu_fast(fmaf(abv.x, x.x, abv.y));
+                    g1 *= dsilu_fast(fmaf(abv.z, x.y, abv.w));
+                  }
+                  r10 += g0; r20 = fmaf(g0, x.x, r20);
+                  r11 += g1; r21 = fmaf(g1, x.y, r21);
+                }
+              }
+#pragma unroll
+              for (int o = 8; o <= 16; o <<= 1) {
+                r10 += __shfl_xor_sync(0xffffffffu, r10, o); r11 += __shfl_xor_sync(0xffffffffu, r11, o);
+                r20 += __shfl_xor_sync(0xffffffffu, r20, o); r21 += __shfl_xor_sync(0xffffffffu, r21, o);
+              }
+              if (lane < 8 && n < p.N) {
+                float* rd = p.gn_red + ((size_t)n * p.Cout + ch) * 2;
+                atomicAdd(rd, r10); atomicAdd(rd + 1, r20); atomicAdd(rd + 2, r11); atomicAdd(rd + 3, r21);
+              }
+            }
+          }
+          mbar_arrive(res_empty_bar);   // every epilogue thread, after its reads of the x tile
+        }
         if (p.chan_stats != nullptr) {
           // Per-(image, channel) sum / sum of squares of the STORED bf16 values for the next GroupNorm (nn.py:17-19), read back
           // from the staged tile.  Warp (gs, oct) owns 8 channel pairs of slab gs; lane = rq*8 + pair, rq picks rows
@@ -460,6 +516,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
               u.w = pack_bf16(f[g * 8 + 6], f[g * 8 + 7]);
               *reinterpret_cast<uint4*>(o + g * 8) = u;
             }
+          } else if (p.out_mode == 2) {
+            // fp32 NHWC rows of Cout_pad values (tap-folded head / first-layer input-gradient GEMMs, gathered by tap_gather)
+            float* o = reinterpret_cast<float*>(p.out) + pix * p.Cout_pad + col0;
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+              if (g * 4 < ncols)
+                *reinterpret_cast<float4*>(o + g * 4) = make_float4(f[g * 4] * p.out_scale, f[g * 4 + 1] * p.out_scale, f[g * 4 + 2] * p.out_scale, f[g * 4 + 3] * p.out_scale);
           } else {
             float* o = reinterpret_cast<float*>(p.out) + ((size_t)n * p.Cout) * HW + (size_t)y * p.W + x;
 #pragma unroll
@@ -552,6 +615,24 @@ static int max_active_pairs(size_t smem_bytes) {
   return n;
 }
 
+// pixel-tile geometry of a conv (shared by the plan builder and the fusion predicates)
+static void tile_dims(int H, int W, int* TW, int* TH) {
+  *TW = W >= 16 ? 16 : W;
+  const int rem = *TW > 0 ? kBlockM / *TW : 0;
+  *TH = H >= rem ? rem : H;
+}
+// Can the GroupNorm-backward reduction of this conv's output ride in its epilogue (kdip_conv_desc.gn_*)?
+bool conv_can_fuse_gn_reduce(const kdip_conv_desc* d) {
+  if (getenv("KDIP_UNFUSED_GNRED") != nullptr) return false;
+  if (d->out_mode != 0 || d->res_mode != 0 || d->Cout != d->Cout_pad || d->Cout % 64 != 0) return false;
+  if (d->gn_C0 <= 0 || d->gn_C0 > d->Cout || d->gn_C0 % 64 != 0) return false;
+  if (d->gn_C0 < d->Cout && d->gn_x1 == nullptr) return false;
+  int TW, TH;
+  tile_dims(d->H, d->W, &TW, &TH);
+  if (TW <= 0 || kBlockM % TW != 0 || TH <= 0 || (kBlockM / TW) % TH != 0) return false;
+  return d->W % TW == 0 && d->H % TH == 0;
+}
+
 int conv_plan_build(const kdip_conv_desc* d, ConvPlan* plan) {
   KDIP_REQUIRE(d != nullptr && plan != nullptr, KDIP_EINVAL, "conv: null descriptor");
   KDIP_REQUIRE(d->nseg >= 1 && d->nseg <= 3, KDIP_EINVAL, "conv: nseg must be 1..3 (got %d)", d->nseg);
@@ -560,7 +641,10 @@ int conv_plan_build(const kdip_conv_desc* d, ConvPlan* plan) {
   memset(&p, 0, sizeof(p));
   int BN = 0;
   KDIP_REQUIRE(d->Cout >= 1 && d->Cout <= d->Cout_pad, KDIP_ESHAPE, "conv: Cout=%d > Cout_pad=%d", d->Cout, d->Cout_pad);
-  KDIP_REQUIRE(d->out_mode == 1 || (d->Cout == d->Cout_pad && d->Cout % 32 == 0), KDIP_ESHAPE,
+  KDIP_REQUIRE(d->out_mode >= 0 && d->out_mode <= 2, KDIP_EINVAL, "conv: out_mode must be 0, 1 or 2 (got %d)", d->out_mode);
+  KDIP_REQUIRE(d->out_mode != 2 || (d->Cout_pad % 16 == 0 && d->Cout_pad <= 256 && d->res_mode == 0), KDIP_ESHAPE,
+               "conv: fp32 NHWC output needs Cout_pad a multiple of 16 (<= 256) and no residual");
+  KDIP_REQUIRE(d->out_mode != 0 || (d->Cout == d->Cout_pad && d->Cout % 32 == 0), KDIP_ESHAPE,
                "conv: bf16 NHWC output needs Cout == Cout_pad, multiple of 32 (got %d/%d)", d->Cout, d->Cout_pad);
   KDIP_REQUIRE(d->res_mode == 0 || (d->residual != nullptr && d->out_mode == 0), KDIP_EINVAL,
                "conv: residual needs a pointer and bf16 output");
@@ -595,10 +679,17 @@ int conv_plan_build(const kdip_conv_desc* d, ConvPlan* plan) {
   p.tma_epilogue = (d->out_mode == 0 && BN >= 64 && d->Cout == d->Cout_pad && (d->res_mode == 0 || d->res_mode == 1 || up_ok) &&
                     (d->chan_stats == nullptr || whole_tiles)) ? 1 : 0;
   p.res_tma = (p.tma_epilogue && d->res_mode != 0) ? 1 : 0;
+  if (d->gn_red != nullptr) {
+    KDIP_REQUIRE(conv_can_fuse_gn_reduce(d) && p.tma_epilogue, KDIP_ESHAPE,
+                 "conv: fused GroupNorm-backward reduction needs bf16 NHWC output, no residual, 64-channel source splits and whole pixel tiles");
+    KDIP_REQUIRE(d->gn_x0 != nullptr && d->gn_ab != nullptr && ((uintptr_t)d->gn_x0 % 16) == 0 && ((uintptr_t)d->gn_x1 % 16) == 0, KDIP_EINVAL,
+                 "conv: fused GroupNorm-backward reduction needs 16B-aligned sources and the (A, B) table");
+    p.res_tma = 1;
+  }
   // CTA pairs whenever the pixel tiles pair up
   p.pair = (p.tma_epilogue && (m_tiles % 2 == 0)) ? 1 : 0;
   // tuning switches for A/B measurements (tools/time_unet.py): KDIP_CONV_PAIR=0, KDIP_CONV_TMAEPI=0
-  if (const char* e = getenv("KDIP_CONV_TMAEPI")) { if (atoi(e) == 0) { p.tma_epilogue = 0; p.pair = 0; p.res_tma = 0; } }
+  if (const char* e = getenv("KDIP_CONV_TMAEPI")) { if (atoi(e) == 0 && d->gn_red == nullptr) { p.tma_epilogue = 0; p.pair = 0; p.res_tma = 0; } }
   if (const char* e = getenv("KDIP_CONV_PAIR")) { if (atoi(e) == 0) p.pair = 0; }
   // Two pixel tiles per work item when the N tile is narrow: the SM's L2 read port (~64 B/clk) feeds M128 x N128 x K64 MMAs
   // (256 clk) with 32 KB per k-block = 128 B/clk, i.e. at most half rate; sharing the weight stage between two accumulators
@@ -614,17 +705,21 @@ int conv_plan_build(const kdip_conv_desc* d, ConvPlan* plan) {
     if (atoi(e) == 1) p.mt = 1;
     if (atoi(e) == 2 && p.tma_epilogue && BN <= 128 && m_tiles % 2 == 0) p.mt = 2;
   }
-  if (p.mt == 2) p.pair = 0;
+  // mt = 2 as CTA pairs (four pixel tiles per work item) measured no faster than single CTAs (B200, 128->128 @ 256^2: 613 vs
+  // 585 us): off unless KDIP_CONV_PAIRMT=1 (kept for the parity tests and future tuning)
+  if (p.mt == 2 && (m_tiles % 4 != 0 || !(getenv("KDIP_CONV_PAIRMT") && atoi(getenv("KDIP_CONV_PAIRMT")) == 1))) p.pair = 0;
   p.b_rows = p.pair ? BN / 2 : BN;
-  p.total_work = p.pair ? (m_tiles / 2) * p.n_tiles : (m_tiles / p.mt) * p.n_tiles;
+  p.total_work = (m_tiles / (p.mt * (p.pair ? 2 : 1))) * p.n_tiles;
   p.idesc = umma_idesc_bf16(p.pair ? 2 * kBlockM : kBlockM, BN);
   p.bias = d->bias;
   p.residual = reinterpret_cast<const __nv_bfloat16*>(d->residual);
   p.res_mode = d->res_mode;
   p.out = d->out;
   p.out_mode = d->out_mode;
-  p.out_scale = d->out_mode == 1 ? d->out_scale : 1.0f;
+  p.out_scale = d->out_mode != 0 ? d->out_scale : 1.0f;
   p.chan_stats = d->chan_stats;
+  p.gn_ab = d->gn_ab; p.gn_red = d->gn_red; p.gn_C0 = d->gn_C0; p.gn_silu = d->gn_silu;
+  p.gn_two = (d->gn_red != nullptr && d->gn_x1 != nullptr && d->gn_C0 < d->Cout) ? 1 : 0;
 
   for (int s = 0; s < d->nseg; ++s) {
     const kdip_conv_seg& sg = d->seg[s];
@@ -647,7 +742,16 @@ int conv_plan_build(const kdip_conv_desc* d, ConvPlan* plan) {
     int rc = encode_tmap_bf16_4d(&p.mapOut, d->out, (uint64_t)d->Cout, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N, 64,
                                  (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TN);
     if (rc != KDIP_OK) return rc;
-    if (p.res_tma) {
+    if (d->gn_red != nullptr) {
+      rc = encode_tmap_bf16_4d(&p.mapRes, d->gn_x0, (uint64_t)d->gn_C0, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N, 64,
+                               (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TN);
+      if (rc != KDIP_OK) return rc;
+      if (p.gn_two) {
+        rc = encode_tmap_bf16_4d(&p.mapRes2, d->gn_x1, (uint64_t)(d->Cout - d->gn_C0), (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N, 64,
+                                 (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TN);
+        if (rc != KDIP_OK) return rc;
+      }
+    } else if (p.res_tma) {
       KDIP_REQUIRE(((uintptr_t)d->residual % 16) == 0, KDIP_EALIGN, "conv: residual must be 16B aligned");
       const int sh = d->res_mode == 3 ? 1 : 0;
       rc = encode_tmap_bf16_4d(&p.mapRes, d->residual, (uint64_t)d->Cout, (uint64_t)(d->W >> sh), (uint64_t)(d->H >> sh), (uint64_t)d->N, 64,

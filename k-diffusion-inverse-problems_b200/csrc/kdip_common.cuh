@@ -63,6 +63,21 @@ __device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
   return __bfloat1622float2(v);
 }
 
+// ---- fast activations: SiLU through tanh.approx (rel. error 2^-11, below the bf16 rounding of the stored results) ----
+__device__ __forceinline__ float fast_tanh(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float silu_fast(float u) {
+  const float h = 0.5f * u;
+  return fmaf(h, fast_tanh(h), h);
+}
+// d/du silu(u) = s*(1 + u*(1-s)), s = sigmoid(u) = 0.5 + 0.5*tanh(u/2)
+__device__ __forceinline__ float dsilu_fast(float u) {
+  const float s = fmaf(0.5f, fast_tanh(0.5f * u), 0.5f);
+  return s * fmaf(u, 1.f - s, 1.f);
+}
 // ---- mbarrier ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

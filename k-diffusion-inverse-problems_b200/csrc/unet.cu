@@ -28,6 +28,7 @@ namespace kdip {
 struct ConvPlan;  // conv_gemm.cu
 int conv_plan_build(const kdip_conv_desc* d, ConvPlan* plan);
 int conv_plan_launch(const ConvPlan* plan, cudaStream_t stream);
+bool conv_can_fuse_gn_reduce(const kdip_conv_desc* d);
 ConvPlan* conv_plan_new();
 void conv_plan_free(ConvPlan* p);
 
@@ -98,6 +99,7 @@ struct kdip_unet {
   std::vector<AttnWeights> attw;
   bf16 *w_in_i2c = nullptr, *w_headd_i2c = nullptr;        // im2col GEMM weights [C0][64] (first conv, head input-gradient)
   bf16 *w_ind = nullptr, *w_head = nullptr, *w_cov = nullptr;
+  bf16 *w_head_fold = nullptr, *w_ind_fold = nullptr;       // tap-folded [64][C0] / [32][C0] (unet_kernels.cu::tap_gather)
   const float *b_in = nullptr, *b_head = nullptr, *b_cov = nullptr, *g_head = nullptr, *be_head = nullptr;
   float *wall = nullptr, *ball = nullptr;      // concatenated emb_layers
   int R = 0;                                   // rows of the emb_proj table
@@ -126,6 +128,8 @@ struct kdip_unet {
   float *head_out = nullptr, *cov_out_ptr = nullptr, *ind_out = nullptr;
   const void* hlast_ptr = nullptr;   // pre-head feature (bf16 NHWC)
   const void* scrA_ptr = nullptr;    // normalised head input
+  void* scrB_ptr = nullptr;          // free scratch at head time: tap-folded head GEMM output P (fp32 [N*S*S][64])
+  void* g3_ptr = nullptr;            // free scratch at the end of the VJP: P of the first layer's input-gradient (fp32 [N*S*S][32])
   const void* gin_final = nullptr;   // gradient wrt the first conv's output
 };
 
@@ -298,6 +302,8 @@ extern "C" int kdip_unet_create(const kdip_unet_arch* arch, int n_tensors, const
       TRY(launch_pack_im2col_weight(w, b.cout, 3, 0, b.cout, u->w_in_i2c, s));
       TRY(keep(p + ".bias", b.cout, &u->b_in));
       TRY(pack(p + ".weight", b.cout, 3, 0, 3, 9, 1, &u->w_ind));   // dgrad: rows = 3 (pad 16), cols = cout
+      TRY(dev_alloc(u, (size_t)32 * b.cout * 2, (void**)&u->w_ind_fold));
+      TRY(launch_fold_taps(u->w_ind, 16, 3, b.cout, 32, u->w_ind_fold, s));
     } else if (b.kind == 1) {
       ResWeights& rw = u->resw[i];
       memset(&rw, 0, sizeof(rw));
@@ -354,6 +360,8 @@ extern "C" int kdip_unet_create(const kdip_unet_arch* arch, int n_tensors, const
     TRY(keep("out.0.weight", c0, &u->g_head));
     TRY(keep("out.0.bias", c0, &u->be_head));
     TRY(pack("out.2.weight", 6, c0, 0, c0, 9, 0, &u->w_head));      // rows 6 -> 16
+    TRY(dev_alloc(u, (size_t)64 * c0 * 2, (void**)&u->w_head_fold));
+    TRY(launch_fold_taps(u->w_head, 16, 6, c0, 64, u->w_head_fold, s));
     const float* hb;
     TRY(get("out.2.bias", 6, &hb));
     float* hb16;
@@ -719,9 +727,12 @@ static int build_launch_plan(kdip_unet* u, int N, void* ws, size_t ws_bytes, siz
         dh.N = N; dh.H = H; dh.W = H; dh.Cout_pad = c0; dh.Cout = c0; dh.nseg = 1;
         dh.seg[0].act = g3; dh.seg[0].C = 64; dh.seg[0].wgt = u->w_headd_i2c; dh.seg[0].taps = 1;
         dh.out = g2; dh.out_mode = 0; dh.out_scale = 1.f;
+        dh.gn_x0 = hlast.p; dh.gn_C0 = c0; dh.gn_silu = 1; dh.gn_ab = ab_head; dh.gn_red = red;
+        const bool fused = conv_can_fuse_gn_reduce(&dh);
+        if (!fused) dh.gn_red = nullptr;
         add_conv_op(K, conv(dh));
+        if (!fused) K.push_back([=](cudaStream_t s) { return launch_gn_bwd_reduce(hlast.p, c0, nullptr, 0, n, hh, hh, ab_head, 1, RS_NONE, g2, red, s); });
       }
-      K.push_back([=](cudaStream_t s) { return launch_gn_bwd_reduce(hlast.p, c0, nullptr, 0, n, hh, hh, ab_head, 1, RS_NONE, g2, red, s); });
       K.push_back([=](cudaStream_t s) { return launch_gn_bwd_finalize(red, ab_head, mr_head, nullptr, n, c0, hh * hh, nullptr, 0, 0, kbuf, s); });
       K.push_back([=](cudaStream_t s) { return launch_gn_bwd_apply(hlast.p, c0, nullptr, 0, n, hh, hh, ab_head, kbuf, 1, RS_NONE, g2, nullptr, 0, gin, nullptr, s); });
     }
@@ -748,12 +759,15 @@ static int build_launch_plan(kdip_unet* u, int N, void* ws, size_t ws_bytes, siz
         d.N = N; d.H = Ho; d.W = Ho; d.Cout_pad = cout; d.Cout = cout; d.nseg = 1;
         d.seg[0].act = gi; d.seg[0].C = cout; d.seg[0].wgt = w.w2d; d.seg[0].taps = 9;
         d.out = g2; d.out_mode = 0; d.out_scale = 1.f;
-        add_conv_op(K, conv(d));
-        // GN2 backward: (h1, g_a2) -> g_h1 (g3)
+        // GN2 backward: (h1, g_a2) -> g_h1 (g3); its reduction pass rides in the dgrad conv's epilogue
         float* red2 = take_red(cout);
         Act h1 = sr.h1;
         float *ab2 = sr.ab2, *mr2 = sr.mr2;
-        K.push_back([=](cudaStream_t s) { return launch_gn_bwd_reduce(h1.p, cout, nullptr, 0, n, Ho, Ho, ab2, 1, RS_NONE, g2, red2, s); });
+        d.gn_x0 = h1.p; d.gn_C0 = cout; d.gn_silu = 1; d.gn_ab = ab2; d.gn_red = red2;
+        const bool fused2 = conv_can_fuse_gn_reduce(&d);
+        if (!fused2) d.gn_red = nullptr;
+        add_conv_op(K, conv(d));
+        if (!fused2) K.push_back([=](cudaStream_t s) { return launch_gn_bwd_reduce(h1.p, cout, nullptr, 0, n, Ho, Ho, ab2, 1, RS_NONE, g2, red2, s); });
         K.push_back([=](cudaStream_t s) { return launch_gn_bwd_finalize(red2, ab2, mr2, nullptr, n, cout, Ho * Ho, nullptr, 0, 0, kbuf, s); });
         K.push_back([=](cudaStream_t s) { return launch_gn_bwd_apply(h1.p, cout, nullptr, 0, n, Ho, Ho, ab2, kbuf, 1, RS_NONE, g2, nullptr, 0, g3, nullptr, s); });
         // dgrad conv1: g_h1 -> g_a1 (g2), Cin channels at the output resolution
@@ -761,6 +775,13 @@ static int build_launch_plan(kdip_unet* u, int N, void* ws, size_t ws_bytes, siz
         d.N = N; d.H = Ho; d.W = Ho; d.Cout_pad = cin; d.Cout = cin; d.nseg = 1;
         d.seg[0].act = g3; d.seg[0].C = cout; d.seg[0].wgt = w.w1d; d.seg[0].taps = 9;
         d.out = g2; d.out_mode = 0; d.out_scale = 1.f;
+        float* red1 = take_red(cin);
+        bool fused1 = false;
+        if (rs == RS_NONE) {     // same-resolution GroupNorm input: fuse the reduction of GN1's backward
+          d.gn_x0 = sr.src0.p; d.gn_C0 = sr.src0.C; d.gn_x1 = sr.src1.p; d.gn_silu = 1; d.gn_ab = sr.ab1; d.gn_red = red1;
+          fused1 = conv_can_fuse_gn_reduce(&d);
+          if (!fused1) d.gn_red = nullptr;
+        }
         add_conv_op(K, conv(d));
         // skip path
         const bf16* extra = gi;
@@ -775,12 +796,11 @@ static int build_launch_plan(kdip_unet* u, int N, void* ws, size_t ws_bytes, siz
           extra_mode = 1;
         }
         // GN1 backward (+resample^T) + skip gradient -> gradients of the (one or two) sources
-        float* red1 = take_red(cin);
         Act s0 = sr.src0, s1 = sr.src1;
         float *ab1 = sr.ab1, *mr1 = sr.mr1;
         bf16* dst0 = gfree;
         bf16* dst1 = sr.two ? hs_grad[rec.pop_id] : nullptr;
-        K.push_back([=](cudaStream_t s) { return launch_gn_bwd_reduce(s0.p, s0.C, s1.p, s1.C, n, Hin, Hin, ab1, 1, rs, g2, red1, s); });
+        if (!fused1) K.push_back([=](cudaStream_t s) { return launch_gn_bwd_reduce(s0.p, s0.C, s1.p, s1.C, n, Hin, Hin, ab1, 1, rs, g2, red1, s); });
         K.push_back([=](cudaStream_t s) { return launch_gn_bwd_finalize(red1, ab1, mr1, nullptr, n, cin, Hin * Hin, nullptr, 0, 0, kbuf, s); });
         K.push_back([=](cudaStream_t s) {
           return launch_gn_bwd_apply(s0.p, s0.C, s1.p, s1.C, n, Hin, Hin, ab1, kbuf, 1, rs, g2, extra, extra_mode, dst0, dst1, s);
@@ -804,10 +824,13 @@ static int build_launch_plan(kdip_unet* u, int N, void* ws, size_t ws_bytes, siz
         d.N = N; d.H = hh; d.W = hh; d.Cout_pad = c; d.Cout = c; d.nseg = 1;
         d.seg[0].act = g3; d.seg[0].C = 3 * c; d.seg[0].wgt = w.wqkvd; d.seg[0].taps = 1;
         d.out = g2; d.out_mode = 0; d.out_scale = 1.f;
-        add_conv_op(K, conv(d));                                     // g_a (g2)
         float* red = take_red(c);
+        d.gn_x0 = x.p; d.gn_C0 = c; d.gn_silu = 0; d.gn_ab = ab; d.gn_red = red;
+        const bool fuseda = conv_can_fuse_gn_reduce(&d);
+        if (!fuseda) d.gn_red = nullptr;
+        add_conv_op(K, conv(d));                                     // g_a (g2)
         bf16* dst0 = gfree;
-        K.push_back([=](cudaStream_t s) { return launch_gn_bwd_reduce(x.p, c, nullptr, 0, n, hh, hh, ab, 0, RS_NONE, g2, red, s); });
+        if (!fuseda) K.push_back([=](cudaStream_t s) { return launch_gn_bwd_reduce(x.p, c, nullptr, 0, n, hh, hh, ab, 0, RS_NONE, g2, red, s); });
         K.push_back([=](cudaStream_t s) { return launch_gn_bwd_finalize(red, ab, mr, nullptr, n, c, T, nullptr, 0, 0, kbuf, s); });
         K.push_back([=](cudaStream_t s) { return launch_gn_bwd_apply(x.p, c, nullptr, 0, n, hh, hh, ab, kbuf, 0, RS_NONE, g2, gi, 1, dst0, nullptr, s); });
         std::swap(gin, gfree);
@@ -825,6 +848,8 @@ static int build_launch_plan(kdip_unet* u, int N, void* ws, size_t ws_bytes, siz
     if (B.cur > ws_bytes) { set_error("unet: workspace too small: need %zu bytes, got %zu", B.cur, ws_bytes); return KDIP_ENOMEM; }
     u->planned_N = N; u->planned_ws = ws; u->planned_bytes = ws_bytes;
     u->scrA_ptr = scrA;
+    u->scrB_ptr = scrB;
+    u->g3_ptr = g3;
     u->hlast_ptr = hlast.p;
   }
   return KDIP_OK;
@@ -929,18 +954,21 @@ static int forward_tail(kdip_unet* u, int N, float* out, float* cov_out, cudaStr
   int rc;
   const int S = u->arch.image_size, c0 = (int)(u->arch.channel_mult[0] * u->arch.model_channels);
   if (flops) *flops = 2.0 * N * S * S * 6.0 * c0 * 9;
-  if (u->head_plan == nullptr || u->head_out != out) {
+  if (u->head_plan == nullptr) {   // output goes to scratch: the plan no longer depends on the caller's pointer
     kdip_conv_desc d;
     memset(&d, 0, sizeof(d));
-    d.N = N; d.H = S; d.W = S; d.Cout_pad = 16; d.Cout = 6; d.nseg = 1;
-    d.seg[0].act = u->scrA_ptr; d.seg[0].C = c0; d.seg[0].wgt = u->w_head; d.seg[0].taps = 9;
-    d.bias = u->b_head; d.out = out; d.out_mode = 1; d.out_scale = 1.f;
+    // head conv3x3 C0 -> 6 (unet.py:617) as a tap-folded 1x1 GEMM (N = 54 -> 64) into scratch + 9-neighbour gather
+    d.N = N; d.H = S; d.W = S; d.Cout_pad = 64; d.Cout = 64; d.nseg = 1;
+    d.seg[0].act = u->scrA_ptr; d.seg[0].C = c0; d.seg[0].wgt = u->w_head_fold; d.seg[0].taps = 1;
+    d.out = u->scrB_ptr; d.out_mode = 2; d.out_scale = 1.f;
     ConvPlan* p = make_conv(u, d, &rc);
     if (rc != KDIP_OK) return rc;
     retire_plan(u, u->head_plan);
     u->head_plan = p; u->head_out = out;
   }
   rc = conv_plan_launch(u->head_plan, s);
+  if (rc != KDIP_OK) return rc;
+  rc = launch_tap_gather((const float*)u->scrB_ptr, 64, u->b_head, N, 6, S, S, out, s);
   if (rc != KDIP_OK) return rc;
   if (cov_out) {
     if (u->cov_plan == nullptr || u->cov_out_ptr != cov_out) {
@@ -980,18 +1008,21 @@ static int vjp_tail(kdip_unet* u, int N, float* grad_x, cudaStream_t s, double* 
   int rc;
   const int S = u->arch.image_size, c0 = (int)(u->arch.channel_mult[0] * u->arch.model_channels);
   if (flops) *flops = 2.0 * N * S * S * 3.0 * c0 * 9;
-  if (u->ind_plan == nullptr || u->ind_out != grad_x) {
+  if (u->ind_plan == nullptr) {
     kdip_conv_desc d;
     memset(&d, 0, sizeof(d));
-    d.N = N; d.H = S; d.W = S; d.Cout_pad = 16; d.Cout = 3; d.nseg = 1;
-    d.seg[0].act = u->gin_final; d.seg[0].C = c0; d.seg[0].wgt = u->w_ind; d.seg[0].taps = 9;
-    d.out = grad_x; d.out_mode = 1; d.out_scale = 1.f;
+    // first layer's input-gradient C0 -> 3 as a tap-folded 1x1 GEMM (N = 27 -> 32) into scratch + 9-neighbour gather
+    d.N = N; d.H = S; d.W = S; d.Cout_pad = 32; d.Cout = 32; d.nseg = 1;
+    d.seg[0].act = u->gin_final; d.seg[0].C = c0; d.seg[0].wgt = u->w_ind_fold; d.seg[0].taps = 1;
+    d.out = u->g3_ptr; d.out_mode = 2; d.out_scale = 1.f;
     ConvPlan* p = make_conv(u, d, &rc);
     if (rc != KDIP_OK) return rc;
     retire_plan(u, u->ind_plan);
     u->ind_plan = p; u->ind_out = grad_x;
   }
-  return conv_plan_launch(u->ind_plan, s);
+  rc = conv_plan_launch(u->ind_plan, s);
+  if (rc != KDIP_OK) return rc;
+  return launch_tap_gather((const float*)u->g3_ptr, 32, nullptr, N, 3, S, S, grad_x, s);
 }
 
 extern "C" int kdip_unet_vjp(kdip_unet* u, const float* seed, int N, float* grad_x, void* workspace, size_t ws_bytes,

@@ -141,20 +141,6 @@ int launch_gn_finalize(const float* stats0, int C0, const float* stats1, int C1,
 // and one 16 B store; 4 independent loads are in flight per thread.  SiLU uses tanh.approx (rel. error 2^-11, below the bf16
 // rounding of the stored result): silu(u) = h + h*tanh(h), h = u/2.
 // ---------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float fast_tanh(float x) {
-  float y;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float silu_fast(float u) {
-  const float h = 0.5f * u;
-  return fmaf(h, fast_tanh(h), h);
-}
-// d/du silu(u) = s*(1 + u*(1-s)), s = sigmoid(u) = 0.5 + 0.5*tanh(u/2)
-__device__ __forceinline__ float dsilu_fast(float u) {
-  const float s = fmaf(0.5f, fast_tanh(0.5f * u), 0.5f);
-  return s * fmaf(u, 1.f - s, 1.f);
-}
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
   float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
   f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
@@ -795,6 +781,59 @@ __global__ void pack_small_kernel(const float* __restrict__ w, int O, int I, int
 }
 int launch_pack_small(const float* w_oihw, int O, int I, int flip, float* dst, cudaStream_t s) {
   pack_small_kernel<<<64, 256, 0, s>>>(w_oihw, O, I, flip, dst);
+  KDIP_LAUNCH_CHECK();
+  return KDIP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Tap gather for the 3x3 convs with a tiny OUTPUT-channel count (head 128->6, unet.py:617; first layer's input-gradient 128->3):
+// the GEMM computes every tap's contribution of every pixel once, P[pix][tap*CO + co] (K = Cin, N = 9*CO <= 64, activations
+// read once instead of nine times), and this kernel sums the nine neighbours: out[n,co,y,x] = bias[co] + sum_tap P[(y+dy,x+dx)][tap,co].
+// ---------------------------------------------------------------------------------------------------------------------
+template <int CO>
+__global__ void tap_gather_kernel(const float* __restrict__ P, int ldp, const float* __restrict__ bias, int H, int W, size_t total,
+                                  float* __restrict__ out) {
+  const size_t HW = (size_t)H * W;
+  for (size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x; pix < total; pix += (size_t)gridDim.x * blockDim.x) {
+    const int x = (int)(pix % W), y = (int)((pix / W) % H);
+    const size_t n = pix / HW;
+    float acc[CO];
+#pragma unroll
+    for (int c = 0; c < CO; ++c) acc[c] = bias ? __ldg(bias + c) : 0.f;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+      if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+      const float* q = P + ((n * H + yy) * W + xx) * ldp + tap * CO;
+#pragma unroll
+      for (int c = 0; c < CO; ++c) acc[c] += __ldg(q + c);
+    }
+#pragma unroll
+    for (int c = 0; c < CO; ++c) out[(n * CO + c) * HW + (size_t)y * W + x] = acc[c];
+  }
+}
+int launch_tap_gather(const float* P, int ldp, const float* bias, int N, int CO, int H, int W, float* out, cudaStream_t s) {
+  KDIP_REQUIRE(CO == 3 || CO == 6, KDIP_ESHAPE, "tap_gather: CO must be 3 or 6 (got %d)", CO);
+  KDIP_REQUIRE(ldp >= 9 * CO, KDIP_ESHAPE, "tap_gather: row stride %d < 9*CO", ldp);
+  const size_t total = (size_t)N * H * W;
+  if (CO == 3) tap_gather_kernel<3><<<ew_blocks(total, 256), 256, 0, s>>>(P, ldp, bias, H, W, total, out);
+  else tap_gather_kernel<6><<<ew_blocks(total, 256), 256, 0, s>>>(P, ldp, bias, H, W, total, out);
+  KDIP_LAUNCH_CHECK();
+  return KDIP_OK;
+}
+// folded GEMM weights: dst[tap*CO + co][:] = src[tap*rows_pad + co][:]  (src = pack_weight layout [9*rows_pad][cols], bf16)
+__global__ void fold_taps_kernel(const bf16* __restrict__ src, int rows_pad, int CO, int cols, int dst_rows, bf16* __restrict__ dst) {
+  const int total = dst_rows * cols;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int r = i / cols, c = i - r * cols;
+    bf16 v = __float2bfloat16(0.f);
+    if (r < 9 * CO) v = src[(size_t)((r / CO) * rows_pad + (r % CO)) * cols + c];
+    dst[i] = v;
+  }
+}
+int launch_fold_taps(const bf16* src, int rows_pad, int CO, int cols, int dst_rows, bf16* dst, cudaStream_t s) {
+  KDIP_REQUIRE(9 * CO <= dst_rows, KDIP_ESHAPE, "fold_taps: 9*CO=%d exceeds %d rows", 9 * CO, dst_rows);
+  fold_taps_kernel<<<64, 256, 0, s>>>(src, rows_pad, CO, cols, dst_rows, dst);
   KDIP_LAUNCH_CHECK();
   return KDIP_OK;
 }

@@ -55,6 +55,11 @@ int launch_pack_small(const float* w_oihw, int O, int I, int flip, float* dst, c
 int launch_im2col3x3(const float* in, const float* in_scale, int N, int CIN, int H, int W, bf16* out, cudaStream_t s);
 int launch_pack_im2col_weight(const float* w_oihw, int O, int I, int flip, int rows_pad, bf16* dst, cudaStream_t s);
 
+// 3x3 convs with <= 7 OUTPUT channels as a tap-folded 1x1 GEMM (P fp32 [N*H*W][ldp], column tap*CO + co) + this 9-neighbour gather
+// into fp32 NCHW [N,CO,H,W] (+ bias[CO] or NULL); and the folded weights [dst_rows][cols] from the pack_weight layout.
+int launch_tap_gather(const float* P, int ldp, const float* bias, int N, int CO, int H, int W, float* out, cudaStream_t s);
+int launch_fold_taps(const bf16* src, int rows_pad, int CO, int cols, int dst_rows, bf16* dst, cudaStream_t s);
+
 // timestep embedding (nn.py:103-121) + time_embed MLP (unet.py:473-477): semb[N][ted] = SiLU(W2 SiLU(W1 e(t) + b1) + b2)
 int launch_time_embed(const float* t, int N, int mc, const float* w1, const float* b1, const float* w2, const float* b2,
                       float* semb, cudaStream_t s);

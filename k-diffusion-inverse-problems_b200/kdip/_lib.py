@@ -97,7 +97,9 @@ class ConvDesc(ctypes.Structure):
     _fields_ = [("N", ctypes.c_int), ("H", ctypes.c_int), ("W", ctypes.c_int), ("Cout_pad", ctypes.c_int),
                 ("Cout", ctypes.c_int), ("nseg", ctypes.c_int), ("seg", ConvSeg * 3), ("bias", ctypes.c_void_p),
                 ("residual", ctypes.c_void_p), ("res_mode", ctypes.c_int), ("out", ctypes.c_void_p),
-                ("out_mode", ctypes.c_int), ("out_scale", ctypes.c_float), ("chan_stats", ctypes.c_void_p)]
+                ("out_mode", ctypes.c_int), ("out_scale", ctypes.c_float), ("chan_stats", ctypes.c_void_p),
+                ("gn_x0", ctypes.c_void_p), ("gn_x1", ctypes.c_void_p), ("gn_C0", ctypes.c_int), ("gn_silu", ctypes.c_int),
+                ("gn_ab", ctypes.c_void_p), ("gn_red", ctypes.c_void_p)]
 
 
 class UNetArch(ctypes.Structure):

@@ -39,7 +39,7 @@ def pack_weight(w, flip=False, ci_off=0, ci_sub=None):
     return dst, rp
 
 
-def run_conv(segs, N, H, W, cout, bias=None, residual=None, res_mode=0, out_mode=0, out_scale=1.0, stats=None):
+def run_conv(segs, N, H, W, cout, bias=None, residual=None, res_mode=0, out_mode=0, out_scale=1.0, stats=None, gn=None):
     """segs: list of (act bf16 NHWC, packed weight, taps).  Returns the output tensor."""
     d = ConvDesc()
     d.N, d.H, d.W = N, H, W
@@ -68,6 +68,11 @@ def run_conv(segs, N, H, W, cout, bias=None, residual=None, res_mode=0, out_mode
     d.out, d.out_mode, d.out_scale = out.data_ptr(), out_mode, out_scale
     if stats is not None:
         d.chan_stats = stats.data_ptr()
+    if gn is not None:   # fused GroupNorm-backward reduction: (x0 bf16 NHWC, x1 or None, ab [N,C,2], silu, red [N,C,2] zeroed)
+        x0, x1, ab, silu, red = gn
+        d.gn_x0, d.gn_C0, d.gn_silu = x0.data_ptr(), x0.shape[-1], int(silu)
+        d.gn_x1 = x1.data_ptr() if x1 is not None else None
+        d.gn_ab, d.gn_red = ab.data_ptr(), red.data_ptr()
     plan = ctypes.c_void_p()
     check(lib.kdip_conv_plan_create(ctypes.byref(d), ctypes.byref(plan)))
     try:

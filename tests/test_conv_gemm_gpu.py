@@ -125,10 +125,13 @@ def test_conv_nearest_up_skip_tma(case, variant, monkeypatch):
     (2, 32, 32, 192, 64, 1, 1),     # 1x1
     (2, 16, 16, 64, 256, 9, 0),     # Cout 256 -> N tile 128 or 64 with several N tiles per pixel-tile pair
 ], ids=lambda c: "x".join(map(str, c)))
-def test_conv_two_tiles_per_work_item(case, monkeypatch):
-    """mt = 2: two M=128 accumulators share every weight stage (forced on small shapes through KDIP_CONV_MT=2)."""
+@pytest.mark.parametrize("pairmt", ["1", "0"])
+def test_conv_two_tiles_per_work_item(case, pairmt, monkeypatch):
+    """mt = 2: two M=128 accumulators share every weight stage (forced on small shapes through KDIP_CONV_MT=2), as single
+    CTAs and as CTA pairs (four pixel tiles per work item)."""
     from gpu_util import pack_weight, run_conv, to_nchw_f32, to_nhwc_bf16, relerr
     monkeypatch.setenv("KDIP_CONV_MT", "2")
+    monkeypatch.setenv("KDIP_CONV_PAIRMT", pairmt)
     N, H, W, Ci, Co, taps, res = case
     k = 3 if taps == 9 else 1
     x = _mk(N, Ci, H, W, 1)
@@ -146,6 +149,44 @@ def test_conv_two_tiles_per_work_item(case, monkeypatch):
     assert e < TOL
     assert torch.allclose(stats[..., 0], got.sum((2, 3)), rtol=1e-3, atol=2e-2)
     assert torch.allclose(stats[..., 1], (got * got).sum((2, 3)), rtol=1e-3, atol=2e-2)
+
+
+@pytest.mark.parametrize("case", [
+    (2, 16, 16, 64, 128, 0, 1, 9),     # one source, SiLU
+    (3, 8, 8, 128, 192, 128, 1, 9),    # two sources (128 + 64), TN=2 with an out-of-range image
+    (2, 32, 32, 192, 128, 64, 1, 9),   # two sources (64 + 64), CTA pairs / two tiles per work item
+    (2, 16, 16, 192, 256, 0, 0, 1),    # attention: identity activation, 1x1 (qkv input-gradient)
+], ids=lambda c: "x".join(map(str, c)))
+def test_conv_fused_groupnorm_backward_reduction(case):
+    """kdip_conv_desc.gn_*: red[n][c] = (sum g_u, sum g_u x), g_u = g act'(A x + B), over the stored (bf16) conv output g."""
+    from gpu_util import pack_weight, run_conv, to_nchw_f32, to_nhwc_bf16, relerr
+    N, H, W, Ci, C, C0, silu, taps = case
+    k = 3 if taps == 9 else 1
+    gin = _mk(N, Ci, H, W, 1)
+    w = _mk(C, Ci, k, k, 2) / (Ci * taps) ** 0.5
+    x = _mk(N, C, H, W, 3) * 1.3 + 0.2
+    ab = torch.stack([1 + 0.2 * _mk(N, C, 1, 1, 4).flatten(0), 0.3 * _mk(N, C, 1, 1, 5).flatten(0)], -1).reshape(N, C, 2).contiguous()
+    red = torch.zeros(N, C, 2, device="cuda")
+    if C0:
+        x0, x1 = to_nhwc_bf16(x[:, :C0].contiguous()), to_nhwc_bf16(x[:, C0:].contiguous())
+    else:
+        x0, x1 = to_nhwc_bf16(x), None
+    out = run_conv([(to_nhwc_bf16(gin), pack_weight(w)[0], taps)], N, H, W, C, gn=(x0, x1, ab, silu, red))
+    g = to_nchw_f32(out)
+    ref_out = F.conv2d(_bf(gin), _bf(w), padding=k // 2)
+    assert relerr(g, ref_out) < TOL
+    xb = _bf(x)
+    u = ab[:, :, 0, None, None] * xb + ab[:, :, 1, None, None]
+    if silu:
+        sg = torch.sigmoid(u)
+        gu = g * (sg * (1 + u * (1 - sg)))
+    else:
+        gu = g
+    r1, r2 = gu.sum((2, 3)), (gu * xb).sum((2, 3))
+    scale = max(r1.abs().max().item(), r2.abs().max().item())
+    e1, e2 = (red[..., 0] - r1).abs().max().item() / scale, (red[..., 1] - r2).abs().max().item() / scale
+    print(f"fused GN-bwd reduction {case}: rel err {e1:.2e} {e2:.2e}")
+    assert e1 < 2e-3 and e2 < 2e-3     # tanh.approx SiLU' (2^-11) on bf16 operands, fp32 accumulation
 
 
 def test_conv_three_segments():
