@@ -34,6 +34,15 @@ static constexpr int kEpiThreads = 256;
 static constexpr int kSlabBytes = kBlockM * 128;        // one 64-channel bf16 slab of the output tile: 16 KiB
 static constexpr int kStagingBytes = 2 * kSlabBytes;    // 128 channels at a time
 static constexpr int kMaxStages = 8;
+// "halo" pipeline (3x3 convs on images at least 128 pixels wide): a pixel tile is 128 consecutive pixels of ONE image row and a
+// work item is two vertically adjacent tiles.  Per 64-channel chunk the producer loads the four input rows y-1..y+2 once, 130
+// pixels wide (x0-1 .. x0+128, zero-filled outside the image), and all nine taps of both tiles read them through shared-memory
+// descriptors that start dx+1 rows into the slot (the operand swizzle follows the absolute address): 66 KB of activations per chunk and work
+// item instead of 2 x 9 x 16 KB.  Weights stream through their own ring, one (tap, chunk) slab per stage.
+static constexpr int kHaloPix = 130;
+static constexpr int kHaloRowBytes = kHaloPix * 128;    // 16640 B landed by TMA
+static constexpr int kHaloSlot = 17 * 1024;             // slot stride (keeps every slot 1024-byte aligned)
+static constexpr int kHaloSlots = 6;                    // four rows of the current chunk + two of the next
 
 struct ConvParams {
   CUtensorMap mapA[3];
@@ -44,6 +53,9 @@ struct ConvParams {
   int tma_epilogue;     // 1: 8-warp TMA-store epilogue; 0: legacy 4-warp epilogue
   int pair;             // 1: CTA pairs (cta_group::2, M = 256 per pair, B split across the two CTAs)
   int mt;               // pixel tiles per work item (1 or 2): mt = 2 shares every weight stage between two M=128 accumulators
+  int halo;             // 1: halo pipeline (see kHaloPix)
+  int halo_bo;          // 1: descriptors carry the matrix base offset (probe only; wrong on B200, see conv_plan_build)
+  uint32_t res_slab_bytes;   // bytes TMA lands per 64-channel slab of the skip / GroupNorm-source tile
   int b_rows;           // weight rows each CTA loads per k-block: BN (single) or BN/2 (pair)
   int total_work;       // persistent-loop trip count: tiles (single) or pair tiles (pair)
   int seg_taps[3];
@@ -77,6 +89,15 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile) 
   int nt = tile % p.n_tiles;
   int mt = tile / p.n_tiles;
   t.nn0 = nt * p.BN;
+  if (p.halo) {
+    // pixel tiles 2q and 2q+1 are rows 2yp and 2yp+1 of the same 128-pixel column block
+    const int j = mt & 1, q = mt >> 1;
+    const int tx = q % p.tiles_x, r = q / p.tiles_x, hh = p.H >> 1;
+    t.x0 = tx * 128;
+    t.y0 = 2 * (r % hh) + j;
+    t.n0 = r / hh;
+    return t;
+  }
   int tx = mt % p.tiles_x;
   int r = mt / p.tiles_x;
   int ty = r % p.tiles_y;
@@ -101,7 +122,7 @@ __device__ __forceinline__ int work_to_tile(const ConvParams& p, int work, int r
   return m * p.n_tiles + nt;
 }
 
-template <bool kPair>
+template <bool kPair, bool kHalo>
 __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment required by the 128B swizzle atoms (TMA destination and UMMA descriptors)
@@ -114,7 +135,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   const int rank = kPair ? (int)cluster_ctarank() : 0;
   const int work0 = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int work_stride = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  uint8_t* staging = smem + p.num_stages * stage_bytes;                       // [2][128 rows][128 B], TMA-store source
+  // halo mode: [kHaloSlots activation-row slots][num_stages weight stages of BN x 128 B]
+  uint8_t* b_ring = smem + kHaloSlots * kHaloSlot;
+  const int b_stage_bytes = p.b_rows * 128;
+  uint8_t* staging = kHalo ? b_ring + p.num_stages * b_stage_bytes : smem + p.num_stages * stage_bytes;   // [2][128 rows][128 B], TMA-store source
   uint8_t* res_stage = staging + (p.tma_epilogue ? kStagingBytes : 0);        // residual tile, same layout
   uint8_t* after = res_stage + (p.res_tma ? kStagingBytes : 0);
   float* bias_s = reinterpret_cast<float*>(after);                            // [256]
@@ -125,6 +149,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   uint64_t* res_full_bar = tmem_empty_bar + 2;
   uint64_t* res_empty_bar = res_full_bar + 1;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_empty_bar + 1);
+  uint64_t* a_full_bar = res_empty_bar + 2;            // halo mode: activation-row slots
+  uint64_t* a_empty_bar = a_full_bar + kHaloSlots;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -151,6 +177,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     }
     mbar_init(res_full_bar, 1);
     mbar_init(res_empty_bar, kEpiThreads);
+    if (kHalo) {
+      for (int s = 0; s < kHaloSlots; ++s) {
+        mbar_init(&a_full_bar[s], kPair ? 2 : 1);   // pair: one arrive.expect_tx per CTA, both on the leader's barrier
+        mbar_init(&a_empty_bar[s], 1);
+      }
+    }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -168,7 +200,34 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (kHalo) {
+      // activation rows: per (segment, 64-channel chunk) the rows y0-1 .. y0+2 (3x3) or y0, y0+1 (1x1) of the work item
+      if (lane == 0) {
+        int slot = 0;
+        uint32_t ph = 0;
+        for (int work = work0; work < p.total_work; work += work_stride) {
+          const TileCoord t = decode_tile(p, work_to_tile(p, work, rank, 0));
+          for (int s = 0; s < p.nseg; ++s) {
+            const int nrows = p.seg_taps[s] == 9 ? 4 : 2;
+            const int ybase = p.seg_taps[s] == 9 ? t.y0 - 1 : t.y0;
+            for (int ch = 0; ch < p.seg_chunks[s]; ++ch) {
+              for (int r = 0; r < nrows; ++r) {
+                mbar_wait(&a_empty_bar[slot], ph ^ 1);
+                if (kPair) {
+                  const uint32_t fb = leader_addr(&a_full_bar[slot]);
+                  mbar_arrive_expect_tx_cluster(fb, (uint32_t)kHaloRowBytes);
+                  tma_load_4d_2sm(smem + slot * kHaloSlot, &p.mapA[s], fb, ch * kBlockK, t.x0 - 1, ybase + r, t.n0);
+                } else {
+                  mbar_arrive_expect_tx(&a_full_bar[slot], (uint32_t)kHaloRowBytes);
+                  tma_load_4d(smem + slot * kHaloSlot, &p.mapA[s], &a_full_bar[slot], ch * kBlockK, t.x0 - 1, ybase + r, t.n0);
+                }
+                if (++slot == kHaloSlots) { slot = 0; ph ^= 1; }
+              }
+            }
+          }
+        }
+      }
+    } else if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t tx_bytes = (uint32_t)stage_bytes;
@@ -205,7 +264,68 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (single thread) =====================
-    if (lane == 0 && rank == 0) {
+    if (kHalo) {
+      if (lane == 0 && rank == 0) {
+        int aslot = 0, bst = 0, acc = 0;
+        uint32_t aph = 0, bph = 0, acc_phase = 0;
+        const uint32_t a_base = smem_u32(smem), b_base = smem_u32(b_ring);
+        auto commit = [](uint64_t* bar) { if (kPair) umma_commit_2sm(bar); else umma_commit(bar); };   // pair: arrives in both CTAs
+        for (int work = work0; work < p.total_work; work += work_stride) {
+          mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+          tc_fence_after();
+          const uint32_t d0 = tmem_base + (uint32_t)(acc * 2 * p.BN), d1 = d0 + (uint32_t)p.BN;
+          uint32_t accum = 0;
+          for (int s = 0; s < p.nseg; ++s) {
+            const bool k3 = p.seg_taps[s] == 9;
+            const int nrows = k3 ? 4 : 2;
+            for (int ch = 0; ch < p.seg_chunks[s]; ++ch) {
+              int rs[4];
+              uint32_t rp[4];
+              for (int r = 0; r < nrows; ++r) {
+                rs[r] = aslot; rp[r] = aph;
+                if (++aslot == kHaloSlots) { aslot = 0; aph ^= 1; }
+              }
+              const int ndy = k3 ? 3 : 1;
+              for (int dyi = 0; dyi < ndy; ++dyi) {
+                // tile 0 (row y0) reads slot row dyi, tile 1 (row y0+1) reads slot row dyi+1
+                if (dyi == 0) mbar_wait(&a_full_bar[rs[0]], rp[0]);
+                mbar_wait(&a_full_bar[rs[dyi + 1]], rp[dyi + 1]);
+                tc_fence_after();
+                const int ndx = k3 ? 3 : 1;
+                for (int dxi = 0; dxi < ndx; ++dxi) {
+                  const uint32_t roff = k3 ? (uint32_t)dxi : 1u;       // rows into the slot: dx + 1
+                  mbar_wait(&full_bar[bst], bph);
+                  tc_fence_after();
+                  const uint32_t bo = p.halo_bo ? roff : 0u;
+                  const uint64_t a0_desc = umma_desc_sw128_bo(a_base + rs[dyi] * kHaloSlot + roff * 128u, bo);
+                  const uint64_t a1_desc = umma_desc_sw128_bo(a_base + rs[dyi + 1] * kHaloSlot + roff * 128u, bo);
+                  const uint64_t b_desc = umma_desc_sw128(b_base + bst * b_stage_bytes);
+#pragma unroll
+                  for (int k = 0; k < kBlockK / 16; ++k) {
+                    if (kPair) {
+                      umma_bf16_ss_2sm(d0, a0_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), p.idesc, accum);
+                      umma_bf16_ss_2sm(d1, a1_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), p.idesc, accum);
+                    } else {
+                      umma_bf16_ss(d0, a0_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), p.idesc, accum);
+                      umma_bf16_ss(d1, a1_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), p.idesc, accum);
+                    }
+                    accum = 1;
+                  }
+                  commit(&empty_bar[bst]);
+                  if (++bst == p.num_stages) { bst = 0; bph ^= 1; }
+                }
+                // rows that no later tap of this chunk reads go back to the producer once the MMAs above retire
+                if (!k3) { commit(&a_empty_bar[rs[0]]); commit(&a_empty_bar[rs[1]]); }
+                else if (dyi < 2) commit(&a_empty_bar[rs[dyi]]);
+                else { commit(&a_empty_bar[rs[2]]); commit(&a_empty_bar[rs[3]]); }
+              }
+            }
+          }
+          commit(&tmem_full_bar[acc]);
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+      }
+    } else if (lane == 0 && rank == 0) {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -241,13 +361,38 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
+  } else if (warp == 2) {
+    // ===================== halo mode: weight producer, one (chunk, tap) slab of BN x 64 per stage =====================
+    if (kHalo && lane == 0) {
+      int st = 0;
+      uint32_t ph = 0;
+      for (int work = work0; work < p.total_work; work += work_stride) {
+        const TileCoord t = decode_tile(p, work_to_tile(p, work, rank, 0));
+        for (int s = 0; s < p.nseg; ++s) {
+          for (int ch = 0; ch < p.seg_chunks[s]; ++ch) {
+            for (int tap = 0; tap < p.seg_taps[s]; ++tap) {
+              mbar_wait(&empty_bar[st], ph ^ 1);
+              if (kPair) {   // this CTA's half of the weight rows
+                const uint32_t fb = leader_addr(&full_bar[st]);
+                mbar_arrive_expect_tx_cluster(fb, (uint32_t)b_stage_bytes);
+                tma_load_2d_2sm(b_ring + st * b_stage_bytes, &p.mapB[s], fb, ch * kBlockK, tap * p.Cout_pad + t.nn0 + rank * p.b_rows);
+              } else {
+                mbar_arrive_expect_tx(&full_bar[st], (uint32_t)b_stage_bytes);
+                tma_load_2d(b_ring + st * b_stage_bytes, &p.mapB[s], &full_bar[st], ch * kBlockK, tap * p.Cout_pad + t.nn0);
+              }
+              if (++st == p.num_stages) { st = 0; ph ^= 1; }
+            }
+          }
+        }
+      }
+    }
   } else if (warp == 3) {
     // ===================== residual producer: TMA-loads the identity-skip tile of every output tile =====================
     if (lane == 0 && p.res_tma) {
       const int n_slabs = p.BN / 64;
       // nearest-up skip (unet.py:107,190-197): the 128-pixel output tile reads a (TH/2 x TW/2) box of the half-resolution source
       const int up = p.res_mode == 3 ? 1 : 0;
-      const uint32_t slab_bytes = up ? kSlabBytes / 4 : kSlabBytes;
+      const uint32_t slab_bytes = p.res_slab_bytes;
       uint32_t it = 0;
       for (int work = work0; work < p.total_work; work += work_stride) {
         for (int j = 0; j < mt; ++j) {
@@ -593,8 +738,10 @@ static int pick_bn(int cout_pad, int m_tiles) {
 static void set_smem_attr() {
   static bool attr_set = false;
   if (attr_set) return;
-  cudaFuncSetAttribute(conv_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  cudaFuncSetAttribute(conv_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaFuncSetAttribute(conv_gemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaFuncSetAttribute(conv_gemm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaFuncSetAttribute(conv_gemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaFuncSetAttribute(conv_gemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   attr_set = true;
 }
 
@@ -611,7 +758,7 @@ static int max_active_pairs(size_t smem_bytes) {
   cfg.attrs = &attr;
   cfg.numAttrs = 1;
   int n = 0;
-  if (cudaOccupancyMaxActiveClusters(&n, conv_gemm_kernel<true>, &cfg) != cudaSuccess) { cudaGetLastError(); return -1; }
+  if (cudaOccupancyMaxActiveClusters(&n, conv_gemm_kernel<true, false>, &cfg) != cudaSuccess) { cudaGetLastError(); return -1; }
   return n;
 }
 
@@ -653,7 +800,17 @@ int conv_plan_build(const kdip_conv_desc* d, ConvPlan* plan) {
   KDIP_REQUIRE(d->chan_stats == nullptr || d->out_mode == 0, KDIP_EINVAL, "conv: chan_stats only with bf16 output");
 
   p.N = d->N; p.H = d->H; p.W = d->W;
-  p.TW = d->W >= 16 ? 16 : d->W;
+  // halo pipeline: a 3x3 first segment on an image at least 128 pixels wide, bf16 NHWC output in 64-channel slabs
+  p.halo = (d->seg[0].taps == 9 && d->W % 128 == 0 && d->H % 2 == 0 && d->out_mode == 0 && d->Cout == d->Cout_pad && d->Cout % 64 == 0 &&
+            d->res_mode != 2) ? 1 : 0;
+  if (const char* e = getenv("KDIP_CONV_HALO")) { if (atoi(e) == 0) p.halo = 0; }
+  if (const char* e = getenv("KDIP_CONV_TMAEPI")) { if (atoi(e) == 0) p.halo = 0; }
+  // Measured on B200 (tools/halo_probe.py): the 128B swizzle of tcgen05.mma operands is a function of the ABSOLUTE shared-memory
+  // address, so a descriptor may start any number of 128-byte rows into a 1024-byte atom with base offset 0; setting the
+  // matrix-base-offset field to the row phase gives wrong products.  KDIP_HALO_BASEOFF=1 re-enables it for that probe only.
+  p.halo_bo = 0;
+  if (const char* e = getenv("KDIP_HALO_BASEOFF")) p.halo_bo = atoi(e) ? 1 : 0;
+  p.TW = p.halo ? 128 : (d->W >= 16 ? 16 : d->W);
   KDIP_REQUIRE(kBlockM % p.TW == 0, KDIP_ESHAPE, "conv: W=%d must be >=16 or a power of two", d->W);
   int rem = kBlockM / p.TW;
   p.TH = d->H >= rem ? rem : d->H;
@@ -663,7 +820,7 @@ int conv_plan_build(const kdip_conv_desc* d, ConvPlan* plan) {
   p.tiles_y = (d->H + p.TH - 1) / p.TH;
   p.tiles_n = (d->N + p.TN - 1) / p.TN;
   const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
-  BN = pick_bn(d->Cout_pad, m_tiles);
+  BN = p.halo ? (d->Cout_pad % 128 == 0 ? 128 : 64) : pick_bn(d->Cout_pad, m_tiles);   // halo: two accumulators per buffer, BN <= 128
   KDIP_REQUIRE(BN > 0, KDIP_ESHAPE, "conv: Cout_pad=%d unsupported (need 16, 32 or a multiple of 64)", d->Cout_pad);
   p.BN = BN;
   p.n_tiles = d->Cout_pad / BN;
@@ -675,7 +832,7 @@ int conv_plan_build(const kdip_conv_desc* d, ConvPlan* plan) {
   // (fused statistics read whole staged tiles: only when the pixel tiles divide the image)
   const bool whole_tiles = (d->W % p.TW == 0) && (d->H % p.TH == 0);
   // nearest-up skips ride the TMA path when every tile maps to a whole half-resolution box
-  const bool up_ok = d->res_mode == 3 && whole_tiles && p.TW % 2 == 0 && p.TH % 2 == 0;
+  const bool up_ok = d->res_mode == 3 && whole_tiles && p.TW % 2 == 0 && (p.TH % 2 == 0 || p.halo);
   p.tma_epilogue = (d->out_mode == 0 && BN >= 64 && d->Cout == d->Cout_pad && (d->res_mode == 0 || d->res_mode == 1 || up_ok) &&
                     (d->chan_stats == nullptr || whole_tiles)) ? 1 : 0;
   p.res_tma = (p.tma_epilogue && d->res_mode != 0) ? 1 : 0;
@@ -708,6 +865,14 @@ int conv_plan_build(const kdip_conv_desc* d, ConvPlan* plan) {
   // mt = 2 as CTA pairs (four pixel tiles per work item) measured no faster than single CTAs (B200, 128->128 @ 256^2: 613 vs
   // 585 us): off unless KDIP_CONV_PAIRMT=1 (kept for the parity tests and future tuning)
   if (p.mt == 2 && (m_tiles % 4 != 0 || !(getenv("KDIP_CONV_PAIRMT") && atoi(getenv("KDIP_CONV_PAIRMT")) == 1))) p.pair = 0;
+  if (p.halo) {
+    KDIP_REQUIRE(p.tma_epilogue, KDIP_EINVAL, "conv: internal error, halo pipeline without the TMA epilogue");
+    // CTA pairs (M = 256 MMAs, weight rows split across the two CTAs) keep the per-SM shared-memory traffic of the N = 128 MMAs
+    // under 128 B/clk: operand reads 96 B/clk + TMA writes ~30 B/clk, against 128 + 46 for single CTAs (measured bound ~75 %)
+    p.mt = 2;
+    p.pair = (m_tiles % 4 == 0) ? 1 : 0;
+    if (const char* e = getenv("KDIP_HALO_PAIR")) { if (atoi(e) == 0) p.pair = 0; }
+  }
   p.b_rows = p.pair ? BN / 2 : BN;
   p.total_work = (m_tiles / (p.mt * (p.pair ? 2 : 1))) * p.n_tiles;
   p.idesc = umma_idesc_bf16(p.pair ? 2 * kBlockM : kBlockM, BN);
@@ -729,8 +894,10 @@ int conv_plan_build(const kdip_conv_desc* d, ConvPlan* plan) {
     KDIP_REQUIRE(((uintptr_t)sg.act % 16) == 0 && ((uintptr_t)sg.wgt % 16) == 0, KDIP_EALIGN, "conv: segment pointers must be 16B aligned");
     p.seg_taps[s] = sg.taps;
     p.seg_chunks[s] = sg.C / kBlockK;
-    int rc = encode_tmap_bf16_4d(&p.mapA[s], sg.act, (uint64_t)sg.C, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N, kBlockK,
-                                 (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TN);
+    int rc = p.halo ? encode_tmap_bf16_4d(&p.mapA[s], sg.act, (uint64_t)sg.C, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N, kBlockK,
+                                          (uint32_t)kHaloPix, 1u, 1u)
+                    : encode_tmap_bf16_4d(&p.mapA[s], sg.act, (uint64_t)sg.C, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N, kBlockK,
+                                          (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TN);
     if (rc != KDIP_OK) return rc;
     rc = encode_tmap_bf16_2d(&p.mapB[s], sg.wgt, (uint64_t)sg.C, (uint64_t)sg.taps * d->Cout_pad, kBlockK, (uint32_t)p.b_rows);
     if (rc != KDIP_OK) return rc;
@@ -754,22 +921,26 @@ int conv_plan_build(const kdip_conv_desc* d, ConvPlan* plan) {
     } else if (p.res_tma) {
       KDIP_REQUIRE(((uintptr_t)d->residual % 16) == 0, KDIP_EALIGN, "conv: residual must be 16B aligned");
       const int sh = d->res_mode == 3 ? 1 : 0;
+      const uint32_t bh = (p.TH >> sh) > 0 ? (uint32_t)(p.TH >> sh) : 1u;     // halo tiles are one row high
       rc = encode_tmap_bf16_4d(&p.mapRes, d->residual, (uint64_t)d->Cout, (uint64_t)(d->W >> sh), (uint64_t)(d->H >> sh), (uint64_t)d->N, 64,
-                               (uint32_t)(p.TW >> sh), (uint32_t)(p.TH >> sh), (uint32_t)p.TN);
+                               (uint32_t)(p.TW >> sh), bh, (uint32_t)p.TN);
       if (rc != KDIP_OK) return rc;
+      p.res_slab_bytes = (uint32_t)(p.TW >> sh) * bh * (uint32_t)p.TN * 128u;
     }
+    if (d->gn_red != nullptr) p.res_slab_bytes = kSlabBytes;
   }
-  const int stage_bytes = p.mt * kABytes + p.b_rows * 128;
-  const int budget = 227 * 1024 - extra - 1024 /*align slack*/ - 256;
+  const int stage_bytes = p.halo ? p.b_rows * 128 : p.mt * kABytes + p.b_rows * 128;
+  const int fixed = p.halo ? kHaloSlots * kHaloSlot : 0;
+  const int budget = 227 * 1024 - extra - 1024 /*align slack*/ - 512 - fixed;
   int stages = budget / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (const char* e = getenv("KDIP_CONV_STAGES")) { const int v = atoi(e); if (v >= 2 && v < stages) stages = v; }
   KDIP_REQUIRE(stages >= 2, KDIP_ESHAPE, "conv: not enough shared memory for a 2-stage pipeline (BN=%d)", BN);
   p.num_stages = stages;
-  plan->smem_bytes = (size_t)stages * stage_bytes + 1024 /*align slack*/ + extra + 256;
+  plan->smem_bytes = (size_t)fixed + (size_t)stages * stage_bytes + 1024 /*align slack*/ + extra + 512;
   if (getenv("KDIP_CONV_DEBUG"))
-    fprintf(stderr, "[kdip conv] N=%d H=%d W=%d Cout=%d K=%d taps=%d nseg=%d BN=%d stages=%d pair=%d mt=%d tmaepi=%d res=%d work=%d smem=%zu\n", d->N, d->H,
-            d->W, d->Cout, d->seg[0].C, d->seg[0].taps, d->nseg, BN, stages, p.pair, p.mt, p.tma_epilogue, d->res_mode, p.total_work, plan->smem_bytes);
+    fprintf(stderr, "[kdip conv] N=%d H=%d W=%d Cout=%d K=%d taps=%d nseg=%d BN=%d stages=%d pair=%d mt=%d halo=%d tmaepi=%d res=%d work=%d smem=%zu\n", d->N, d->H,
+            d->W, d->Cout, d->seg[0].C, d->seg[0].taps, d->nseg, BN, stages, p.pair, p.mt, p.halo, p.tma_epilogue, d->res_mode, p.total_work, plan->smem_bytes);
   int sms = num_sms();
   if (p.pair) {
     // a persistent kernel must be fully co-resident: ask the driver how many CTA pairs fit at this shared-memory size
@@ -797,11 +968,13 @@ int conv_plan_launch(const ConvPlan* plan, cudaStream_t stream) {
     attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
     cfg.attrs = &attr;
     cfg.numAttrs = 1;
-    KDIP_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<true>, plan->params));
+    if (plan->params.halo) KDIP_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<true, true>, plan->params));
+    else KDIP_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<true, false>, plan->params));
     count_launch();
     return KDIP_OK;
   }
-  conv_gemm_kernel<false><<<plan->grid, kThreads, plan->smem_bytes, stream>>>(plan->params);
+  if (plan->params.halo) conv_gemm_kernel<false, true><<<plan->grid, kThreads, plan->smem_bytes, stream>>>(plan->params);
+  else conv_gemm_kernel<false, false><<<plan->grid, kThreads, plan->smem_bytes, stream>>>(plan->params);
   KDIP_LAUNCH_CHECK();
   return KDIP_OK;
 }

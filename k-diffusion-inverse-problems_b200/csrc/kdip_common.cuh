@@ -243,6 +243,12 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                              // layout type SWIZZLE_128B, bits [61,64)
   return d;
 }
+// Same with the matrix-base-offset field (bits [49,52)) set.  Measured on B200: a tile may start any number of 128-byte rows into
+// a 1024-byte swizzle atom with this field left at 0 (the swizzle is applied to the absolute address); non-zero values are only
+// used by tools/halo_probe.py.
+__device__ __forceinline__ uint64_t umma_desc_sw128_bo(uint32_t smem_addr, uint32_t base_off) {
+  return umma_desc_sw128(smem_addr) | ((uint64_t)(base_off & 7u) << 49);
+}
 // Instruction descriptor for kind::f16 with BF16 A/B (K-major both), FP32 D; cute::UMMA::InstrDescriptor bit layout.
 __host__ __device__ inline uint32_t umma_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);

@@ -790,34 +790,60 @@ int launch_pack_small(const float* w_oihw, int O, int I, int flip, float* dst, c
 // the GEMM computes every tap's contribution of every pixel once, P[pix][tap*CO + co] (K = Cin, N = 9*CO <= 64, activations
 // read once instead of nine times), and this kernel sums the nine neighbours: out[n,co,y,x] = bias[co] + sum_tap P[(y+dy,x+dx)][tap,co].
 // ---------------------------------------------------------------------------------------------------------------------
+// One CTA = a 4 x 32 pixel tile: the 6 x 34 halo of P rows is staged in shared memory with coalesced loads (row stride
+// 9*CO + 1 words: consecutive pixels fall into consecutive banks), then thread (pixel, half) sums half of the channels.
+static constexpr int TG_TY = 4, TG_TX = 32;
 template <int CO>
-__global__ void tap_gather_kernel(const float* __restrict__ P, int ldp, const float* __restrict__ bias, int H, int W, size_t total,
-                                  float* __restrict__ out) {
+__global__ void __launch_bounds__(256) tap_gather_kernel(const float* __restrict__ P, int ldp, const float* __restrict__ bias, int H, int W,
+                                                         float* __restrict__ out) {
+  constexpr int NV = 9 * CO, LD = NV + 1, HR = TG_TY + 2, HC = TG_TX + 2;
+  extern __shared__ float tile[];   // [HR*HC][LD]
+  const int n = blockIdx.z, y0 = blockIdx.y * TG_TY, x0 = blockIdx.x * TG_TX;
   const size_t HW = (size_t)H * W;
-  for (size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x; pix < total; pix += (size_t)gridDim.x * blockDim.x) {
-    const int x = (int)(pix % W), y = (int)((pix / W) % H);
-    const size_t n = pix / HW;
-    float acc[CO];
-#pragma unroll
-    for (int c = 0; c < CO; ++c) acc[c] = bias ? __ldg(bias + c) : 0.f;
-#pragma unroll
-    for (int tap = 0; tap < 9; ++tap) {
-      const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
-      if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-      const float* q = P + ((n * H + yy) * W + xx) * ldp + tap * CO;
-#pragma unroll
-      for (int c = 0; c < CO; ++c) acc[c] += __ldg(q + c);
-    }
-#pragma unroll
-    for (int c = 0; c < CO; ++c) out[(n * CO + c) * HW + (size_t)y * W + x] = acc[c];
+  for (int i = threadIdx.x; i < HR * HC * NV; i += blockDim.x) {
+    const int r = i / NV, v = i - r * NV;
+    const int yy = y0 - 1 + r / HC, xx = x0 - 1 + r % HC;
+    float val = 0.f;
+    if (yy >= 0 && yy < H && xx >= 0 && xx < W) val = __ldg(P + ((size_t)n * HW + (size_t)yy * W + xx) * ldp + v);
+    tile[r * LD + v] = val;
   }
+  __syncthreads();
+  // 256 threads = 128 pixels x 2 channel halves
+  const int pix = threadIdx.x & 127, half = threadIdx.x >> 7;
+  const int ty = pix / TG_TX, tx = pix % TG_TX;
+  const int y = y0 + ty, x = x0 + tx;
+  if (y >= H || x >= W) return;
+  constexpr int CH = CO / 2 + (CO & 1);          // channels per half: 3 (CO=6) or 2/1 (CO=3)
+  const int c_lo = half * CH, c_hi = (c_lo + CH < CO) ? c_lo + CH : CO;
+  float acc[CH];
+#pragma unroll
+  for (int c = 0; c < CH; ++c) acc[c] = (bias != nullptr && c_lo + c < c_hi) ? __ldg(bias + c_lo + c) : 0.f;
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const float* q = tile + ((ty + tap / 3) * HC + (tx + tap % 3)) * LD + tap * CO + c_lo;
+#pragma unroll
+    for (int c = 0; c < CH; ++c)
+      if (c_lo + c < c_hi) acc[c] += q[c];
+  }
+#pragma unroll
+  for (int c = 0; c < CH; ++c)
+    if (c_lo + c < c_hi) out[((size_t)n * CO + c_lo + c) * HW + (size_t)y * W + x] = acc[c];
 }
 int launch_tap_gather(const float* P, int ldp, const float* bias, int N, int CO, int H, int W, float* out, cudaStream_t s) {
   KDIP_REQUIRE(CO == 3 || CO == 6, KDIP_ESHAPE, "tap_gather: CO must be 3 or 6 (got %d)", CO);
   KDIP_REQUIRE(ldp >= 9 * CO, KDIP_ESHAPE, "tap_gather: row stride %d < 9*CO", ldp);
-  const size_t total = (size_t)N * H * W;
-  if (CO == 3) tap_gather_kernel<3><<<ew_blocks(total, 256), 256, 0, s>>>(P, ldp, bias, H, W, total, out);
-  else tap_gather_kernel<6><<<ew_blocks(total, 256), 256, 0, s>>>(P, ldp, bias, H, W, total, out);
+  dim3 grid((W + TG_TX - 1) / TG_TX, (H + TG_TY - 1) / TG_TY, N);
+  const size_t smem = (size_t)(TG_TY + 2) * (TG_TX + 2) * (9 * CO + 1) * sizeof(float);
+  if (CO == 3) {
+    tap_gather_kernel<3><<<grid, 256, smem, s>>>(P, ldp, bias, H, W, out);
+  } else {
+    static bool attr = false;
+    if (!attr) {
+      KDIP_CUDA(cudaFuncSetAttribute(tap_gather_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr = true;
+    }
+    tap_gather_kernel<6><<<grid, 256, smem, s>>>(P, ldp, bias, H, W, out);
+  }
   KDIP_LAUNCH_CHECK();
   return KDIP_OK;
 }

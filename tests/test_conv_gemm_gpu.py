@@ -189,6 +189,73 @@ def test_conv_fused_groupnorm_backward_reduction(case):
     assert e1 < 2e-3 and e2 < 2e-3     # tanh.approx SiLU' (2^-11) on bf16 operands, fp32 accumulation
 
 
+HALO_CASES = [
+    # N, H, W, Cin, Cout, residual mode (0 none, 1 identity, 3 nearest-up), extra 1x1 segments
+    (1, 4, 128, 64, 64, 0, 0),
+    (2, 8, 256, 128, 128, 1, 0),      # two column blocks per row, identity skip
+    (1, 6, 128, 128, 192, 0, 0),      # N tile 64 x 3
+    (2, 4, 128, 64, 256, 3, 0),       # two N tiles of 128, nearest-up skip from a [2, 64] source
+    (1, 8, 128, 128, 128, 0, 2),      # conv3x3 + two 1x1 skip segments (channel-changing ResBlock over a concatenated input)
+]
+
+
+@pytest.mark.parametrize("case", HALO_CASES, ids=lambda c: "x".join(map(str, c)))
+@pytest.mark.parametrize("pair", ["1", "0"])
+def test_conv_halo_pipeline(case, pair, monkeypatch):
+    """Halo pipeline (images >= 128 pixels wide): rows y-1..y+2 loaded once per chunk, taps read them at row offsets dx+1;
+    as CTA pairs (four rows per work item, weight rows split) and as single CTAs."""
+    from gpu_util import pack_weight, run_conv, to_nchw_f32, to_nhwc_bf16, relerr
+    monkeypatch.setenv("KDIP_HALO_PAIR", pair)
+    N, H, W, Ci, Co, res, nskip = case
+    x = _mk(N, Ci, H, W, 1)
+    w = _mk(Co, Ci, 3, 3, 2) / (Ci * 9) ** 0.5
+    b = _mk(1, Co, 1, 1, 3).flatten()
+    segs = [(to_nhwc_bf16(x), pack_weight(w)[0], 9)]
+    ref = F.conv2d(_bf(x), _bf(w), b, padding=1)
+    if nskip:
+        C0, C1 = 128, 64
+        s0, s1 = _mk(N, C0, H, W, 7), _mk(N, C1, H, W, 8)
+        ws = _mk(Co, C0 + C1, 1, 1, 9) / (C0 + C1) ** 0.5
+        segs += [(to_nhwc_bf16(s0), pack_weight(ws, ci_off=0, ci_sub=C0)[0], 1), (to_nhwc_bf16(s1), pack_weight(ws, ci_off=C0, ci_sub=C1)[0], 1)]
+        ref = ref + F.conv2d(torch.cat([_bf(s0), _bf(s1)], 1), _bf(ws))
+    r = None
+    if res == 1:
+        r = _mk(N, Co, H, W, 5)
+        ref = ref + _bf(r)
+    elif res == 3:
+        r = _mk(N, Co, H // 2, W // 2, 5)
+        ref = ref + F.interpolate(_bf(r), scale_factor=2, mode="nearest")
+    stats = torch.zeros(N, Co, 2, device="cuda")
+    out = run_conv(segs, N, H, W, Co, bias=b, residual=to_nhwc_bf16(r) if r is not None else None, res_mode=res, stats=stats)
+    got = to_nchw_f32(out)
+    assert torch.isfinite(got).all(), "NaN left in output: some pixels/channels were never written"
+    e = relerr(got, ref)
+    print(f"halo conv {case}: rel err {e:.3e}")
+    if not e < TOL:
+        bad = ((got - ref).abs() > TOL * ref.abs().max())
+        print("  bad fraction", bad.float().mean().item(), "per row", bad.float().mean((0, 1, 3)).tolist(), "per col/16",
+              bad.float().mean((0, 1, 2)).view(-1, 16).mean(1).tolist())
+    assert e < TOL
+    assert torch.allclose(stats[..., 0], got.sum((2, 3)), rtol=1e-3, atol=3e-2)
+    assert torch.allclose(stats[..., 1], (got * got).sum((2, 3)), rtol=1e-3, atol=3e-2)
+
+
+def test_conv_halo_matches_tile_pipeline():
+    """Same conv through the halo pipeline and (KDIP_CONV_HALO=0) the 8x16-tile pipeline: identical up to fp32 summation order."""
+    import os
+    from gpu_util import pack_weight, run_conv, to_nchw_f32, to_nhwc_bf16, relerr
+    N, H, W, Ci, Co = 2, 16, 256, 128, 128
+    x, w = _mk(N, Ci, H, W, 1), _mk(Co, Ci, 3, 3, 2) / (Ci * 9) ** 0.5
+    xa, wp = to_nhwc_bf16(x), pack_weight(w)[0]
+    a = to_nchw_f32(run_conv([(xa, wp, 9)], N, H, W, Co))
+    os.environ["KDIP_CONV_HALO"] = "0"
+    try:
+        b = to_nchw_f32(run_conv([(xa, wp, 9)], N, H, W, Co))
+    finally:
+        del os.environ["KDIP_CONV_HALO"]
+    assert relerr(a, b) < 1.0 / 256
+
+
 def test_conv_three_segments():
     """conv3x3(a2) + 1x1 skip over two concatenated sources accumulated in one TMEM tile (unet.py:222,257,662)."""
     from gpu_util import pack_weight, run_conv, to_nchw_f32, to_nhwc_bf16, relerr
