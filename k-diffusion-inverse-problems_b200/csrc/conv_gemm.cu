@@ -55,6 +55,8 @@ struct ConvParams {
   int mt;               // pixel tiles per work item (1 or 2): mt = 2 shares every weight stage between two M=128 accumulators
   int halo;             // 1: halo pipeline (see kHaloPix)
   int halo_bo;          // 1: descriptors carry the matrix base offset (probe only; wrong on B200, see conv_plan_build)
+  int ws;               // 1: the two tiles of a work item share the weight operand through the tensor core's collector (tcgen05.mma.ws)
+  int dbg;              // timing experiments only (KDIP_CONV_DBG): 1 = no operand loads / waits, 2 = epilogue releases TMEM without reading or storing
   uint32_t res_slab_bytes;   // bytes TMA lands per 64-channel slab of the skip / GroupNorm-source tile
   int b_rows;           // weight rows each CTA loads per k-block: BN (single) or BN/2 (pair)
   int total_work;       // persistent-loop trip count: tiles (single) or pair tiles (pair)
@@ -202,7 +204,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     // ===================== TMA producer =====================
     if (kHalo) {
       // activation rows: per (segment, 64-channel chunk) the rows y0-1 .. y0+2 (3x3) or y0, y0+1 (1x1) of the work item
-      if (lane == 0) {
+      if (lane == 0 && !(p.dbg & 1)) {
         int slot = 0;
         uint32_t ph = 0;
         for (int work = work0; work < p.total_work; work += work_stride) {
@@ -288,13 +290,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
               const int ndy = k3 ? 3 : 1;
               for (int dyi = 0; dyi < ndy; ++dyi) {
                 // tile 0 (row y0) reads slot row dyi, tile 1 (row y0+1) reads slot row dyi+1
-                if (dyi == 0) mbar_wait(&a_full_bar[rs[0]], rp[0]);
-                mbar_wait(&a_full_bar[rs[dyi + 1]], rp[dyi + 1]);
+                if (!(p.dbg & 1)) {
+                  if (dyi == 0) mbar_wait(&a_full_bar[rs[0]], rp[0]);
+                  mbar_wait(&a_full_bar[rs[dyi + 1]], rp[dyi + 1]);
+                }
                 tc_fence_after();
                 const int ndx = k3 ? 3 : 1;
                 for (int dxi = 0; dxi < ndx; ++dxi) {
                   const uint32_t roff = k3 ? (uint32_t)dxi : 1u;       // rows into the slot: dx + 1
-                  mbar_wait(&full_bar[bst], bph);
+                  if (!(p.dbg & 1)) mbar_wait(&full_bar[bst], bph);
                   tc_fence_after();
                   const uint32_t bo = p.halo_bo ? roff : 0u;
                   const uint64_t a0_desc = umma_desc_sw128_bo(a_base + rs[dyi] * kHaloSlot + roff * 128u, bo);
@@ -305,6 +309,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                     if (kPair) {
                       umma_bf16_ss_2sm(d0, a0_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), p.idesc, accum);
                       umma_bf16_ss_2sm(d1, a1_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), p.idesc, accum);
+                    } else if (p.ws) {
+                      umma_bf16_ss_ws_fill(d0, a0_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), p.idesc, accum);
+                      umma_bf16_ss_ws_lastuse(d1, a1_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), p.idesc, accum);
                     } else {
                       umma_bf16_ss(d0, a0_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), p.idesc, accum);
                       umma_bf16_ss(d1, a1_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), p.idesc, accum);
@@ -347,6 +354,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             if (kPair) {
               umma_bf16_ss_2sm(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), p.idesc, (kb | k) ? 1u : 0u);
               if (mt == 2) umma_bf16_ss_2sm(d_tmem + (uint32_t)p.BN, a1_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), p.idesc, (kb | k) ? 1u : 0u);
+            } else if (mt == 2 && p.ws) {
+              umma_bf16_ss_ws_fill(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), p.idesc, (kb | k) ? 1u : 0u);
+              umma_bf16_ss_ws_lastuse(d_tmem + (uint32_t)p.BN, a1_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), p.idesc, (kb | k) ? 1u : 0u);
             } else {
               umma_bf16_ss(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), p.idesc, (kb | k) ? 1u : 0u);
               if (mt == 2) umma_bf16_ss(d_tmem + (uint32_t)p.BN, a1_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), p.idesc, (kb | k) ? 1u : 0u);
@@ -363,7 +373,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     }
   } else if (warp == 2) {
     // ===================== halo mode: weight producer, one (chunk, tap) slab of BN x 64 per stage =====================
-    if (kHalo && lane == 0) {
+    if (kHalo && lane == 0 && !(p.dbg & 1)) {
       int st = 0;
       uint32_t ph = 0;
       for (int work = work0; work < p.total_work; work += work_stride) {
@@ -388,7 +398,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     }
   } else if (warp == 3) {
     // ===================== residual producer: TMA-loads the identity-skip tile of every output tile =====================
-    if (lane == 0 && p.res_tma) {
+    if (lane == 0 && p.res_tma && !(p.dbg & 2)) {
       const int n_slabs = p.BN / 64;
       // nearest-up skip (unet.py:107,190-197): the 128-pixel output tile reads a (TH/2 x TW/2) box of the half-resolution source
       const int up = p.res_mode == 3 ? 1 : 0;
@@ -431,6 +441,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     for (int work = work0; work < p.total_work; work += work_stride) {
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
+      if (p.dbg & 2) {
+        tc_fence_before();
+        if (kPair) mbar_arrive_cluster(leader_addr(&tmem_empty_bar[acc])); else mbar_arrive(&tmem_empty_bar[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        continue;
+      }
      for (int mj = 0; mj < mt; ++mj) {
       const TileCoord t = decode_tile(p, work_to_tile(p, work, rank, mj));
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * mt + mj) * p.BN);
@@ -803,11 +819,17 @@ int conv_plan_build(const kdip_conv_desc* d, ConvPlan* plan) {
   // halo pipeline: a 3x3 first segment on an image at least 128 pixels wide, bf16 NHWC output in 64-channel slabs
   p.halo = (d->seg[0].taps == 9 && d->W % 128 == 0 && d->H % 2 == 0 && d->out_mode == 0 && d->Cout == d->Cout_pad && d->Cout % 64 == 0 &&
             d->res_mode != 2) ? 1 : 0;
-  if (const char* e = getenv("KDIP_CONV_HALO")) { if (atoi(e) == 0) p.halo = 0; }
+  // Measured on B200 (tools/time_unet.py 32 80, i.e. seconds of back-to-back evaluations under the 1 kW power cap): the halo
+  // pipeline cuts the L2->SM operand traffic by 2.3x and wins 10 % per conv on a cool GPU (558 vs 614 us, 128->128 @ 256^2) but
+  // loses 2-3 % of the whole UNet evaluation in the power-capped steady state the sampler runs in (48.0 vs 47.4 ms).  It stays
+  // opt-in (KDIP_CONV_HALO=1) and under test; the default is the 8x16-tile pipeline with two tiles per work item.
+  if (!(getenv("KDIP_CONV_HALO") && atoi(getenv("KDIP_CONV_HALO")) == 1)) p.halo = 0;
   if (const char* e = getenv("KDIP_CONV_TMAEPI")) { if (atoi(e) == 0) p.halo = 0; }
   // Measured on B200 (tools/halo_probe.py): the 128B swizzle of tcgen05.mma operands is a function of the ABSOLUTE shared-memory
   // address, so a descriptor may start any number of 128-byte rows into a 1024-byte atom with base offset 0; setting the
   // matrix-base-offset field to the row phase gives wrong products.  KDIP_HALO_BASEOFF=1 re-enables it for that probe only.
+  p.dbg = getenv("KDIP_CONV_DBG") ? atoi(getenv("KDIP_CONV_DBG")) : 0;
+  p.ws = getenv("KDIP_CONV_WS") ? atoi(getenv("KDIP_CONV_WS")) : 1;   // weight-stationary pairs: 0.2-2 % faster, bit-identical results
   p.halo_bo = 0;
   if (const char* e = getenv("KDIP_HALO_BASEOFF")) p.halo_bo = atoi(e) ? 1 : 0;
   p.TW = p.halo ? 128 : (d->W >= 16 ? 16 : d->W);
@@ -869,9 +891,12 @@ int conv_plan_build(const kdip_conv_desc* d, ConvPlan* plan) {
     KDIP_REQUIRE(p.tma_epilogue, KDIP_EINVAL, "conv: internal error, halo pipeline without the TMA epilogue");
     // CTA pairs (M = 256 MMAs, weight rows split across the two CTAs) keep the per-SM shared-memory traffic of the N = 128 MMAs
     // under 128 B/clk: operand reads 96 B/clk + TMA writes ~30 B/clk, against 128 + 46 for single CTAs (measured bound ~75 %)
+    // ... in theory.  Measured (B200, 128->128 @ 256^2, B=32): pairs 588 us vs single CTAs 557 us, and even with operand loads
+    // and epilogue switched off (KDIP_CONV_DBG=3) the M=256 x N=128 pair MMAs issue at 1513 TF/s against 1745 for M=128 x N=128:
+    // single CTAs are the default, KDIP_HALO_PAIR=1 selects pairs (kept under test).
     p.mt = 2;
-    p.pair = (m_tiles % 4 == 0) ? 1 : 0;
-    if (const char* e = getenv("KDIP_HALO_PAIR")) { if (atoi(e) == 0) p.pair = 0; }
+    p.pair = 0;
+    if (const char* e = getenv("KDIP_HALO_PAIR")) { if (atoi(e) == 1 && m_tiles % 4 == 0) p.pair = 1; }
   }
   p.b_rows = p.pair ? BN / 2 : BN;
   p.total_work = (m_tiles / (p.mt * (p.pair ? 2 : 1))) * p.n_tiles;

@@ -800,12 +800,19 @@ __global__ void __launch_bounds__(256) tap_gather_kernel(const float* __restrict
   extern __shared__ float tile[];   // [HR*HC][LD]
   const int n = blockIdx.z, y0 = blockIdx.y * TG_TY, x0 = blockIdx.x * TG_TX;
   const size_t HW = (size_t)H * W;
-  for (int i = threadIdx.x; i < HR * HC * NV; i += blockDim.x) {
-    const int r = i / NV, v = i - r * NV;
+  // one warp per halo pixel row of P: lanes read the 9*CO values as coalesced float2 (row bases are 128-byte aligned)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll 4
+  for (int r = warp; r < HR * HC; r += 8) {
     const int yy = y0 - 1 + r / HC, xx = x0 - 1 + r % HC;
-    float val = 0.f;
-    if (yy >= 0 && yy < H && xx >= 0 && xx < W) val = __ldg(P + ((size_t)n * HW + (size_t)yy * W + xx) * ldp + v);
-    tile[r * LD + v] = val;
+    float2 v = make_float2(0.f, 0.f);
+    if (2 * lane < NV && yy >= 0 && yy < H && xx >= 0 && xx < W) {
+      const float* q = P + ((size_t)n * HW + (size_t)yy * W + xx) * ldp + 2 * lane;
+      if (2 * lane + 1 < NV) v = __ldg(reinterpret_cast<const float2*>(q));
+      else v.x = __ldg(q);
+    }
+    if (2 * lane < NV) tile[r * LD + 2 * lane] = v.x;
+    if (2 * lane + 1 < NV) tile[r * LD + 2 * lane + 1] = v.y;
   }
   __syncthreads();
   // 256 threads = 128 pixels x 2 channel halves

@@ -67,7 +67,7 @@ class OperatorHandle:
 
     def __del__(self):
         h = getattr(self, "_h", None)
-        if h:
+        if h and lib is not None:     # at interpreter shutdown the module globals may already be gone
             lib.kdip_op_destroy(h)
             self._h = None
 

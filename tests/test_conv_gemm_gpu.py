@@ -132,6 +132,7 @@ def test_conv_two_tiles_per_work_item(case, pairmt, monkeypatch):
     from gpu_util import pack_weight, run_conv, to_nchw_f32, to_nhwc_bf16, relerr
     monkeypatch.setenv("KDIP_CONV_MT", "2")
     monkeypatch.setenv("KDIP_CONV_PAIRMT", pairmt)
+    monkeypatch.setenv("KDIP_CONV_WS", "1" if case[0] % 2 == 0 else "0")   # weight-stationary MMA pairs and plain pairs
     N, H, W, Ci, Co, taps, res = case
     k = 3 if taps == 9 else 1
     x = _mk(N, Ci, H, W, 1)
@@ -205,6 +206,7 @@ def test_conv_halo_pipeline(case, pair, monkeypatch):
     """Halo pipeline (images >= 128 pixels wide): rows y-1..y+2 loaded once per chunk, taps read them at row offsets dx+1;
     as CTA pairs (four rows per work item, weight rows split) and as single CTAs."""
     from gpu_util import pack_weight, run_conv, to_nchw_f32, to_nhwc_bf16, relerr
+    monkeypatch.setenv("KDIP_CONV_HALO", "1")
     monkeypatch.setenv("KDIP_HALO_PAIR", pair)
     N, H, W, Ci, Co, res, nskip = case
     x = _mk(N, Ci, H, W, 1)
@@ -241,16 +243,16 @@ def test_conv_halo_pipeline(case, pair, monkeypatch):
 
 
 def test_conv_halo_matches_tile_pipeline():
-    """Same conv through the halo pipeline and (KDIP_CONV_HALO=0) the 8x16-tile pipeline: identical up to fp32 summation order."""
+    """Same conv through the 8x16-tile pipeline and (KDIP_CONV_HALO=1) the halo pipeline: identical up to fp32 summation order."""
     import os
     from gpu_util import pack_weight, run_conv, to_nchw_f32, to_nhwc_bf16, relerr
     N, H, W, Ci, Co = 2, 16, 256, 128, 128
     x, w = _mk(N, Ci, H, W, 1), _mk(Co, Ci, 3, 3, 2) / (Ci * 9) ** 0.5
     xa, wp = to_nhwc_bf16(x), pack_weight(w)[0]
-    a = to_nchw_f32(run_conv([(xa, wp, 9)], N, H, W, Co))
-    os.environ["KDIP_CONV_HALO"] = "0"
+    b = to_nchw_f32(run_conv([(xa, wp, 9)], N, H, W, Co))
+    os.environ["KDIP_CONV_HALO"] = "1"
     try:
-        b = to_nchw_f32(run_conv([(xa, wp, 9)], N, H, W, Co))
+        a = to_nchw_f32(run_conv([(xa, wp, 9)], N, H, W, Co))
     finally:
         del os.environ["KDIP_CONV_HALO"]
     assert relerr(a, b) < 1.0 / 256
