@@ -170,11 +170,30 @@ def run_reference(args):
             "dtype": "f32", "data": "synthetic", "config": workload_config(args, args.gpus),
             "cpu_baseline": dict(value=v, unit="images/s", **info),
             "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Everything libraries print on stdout (e.g. NCCL's version banner) goes to stderr: stdout carries the ONE JSON line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
 
 
 def main():
     args = parse()
+    quiet_stdout()
     if args.impl == "reference":
         return run_reference(args)
     import torch
@@ -288,7 +307,7 @@ def main():
         if n_gpus == 1 and not args.skip_cpu_baseline:
             v, info = cpu_reference_sample(args)
             line["cpu_baseline"] = dict(value=v, unit="images/s", **info)
-        print(json.dumps(line))
+        emit(line)
     if n_gpus > 1:
         import torch.distributed as dist
         dist.barrier()
