@@ -4,6 +4,8 @@
 // Round-1 implementation: fp32 CUDA-core flash-style kernels (scores never leave shared memory; probabilities are
 // recomputed from the saved log-sum-exp in the backward).  Attention is 0.1% of the UNet FLOPs;
 // the tensor-core (tcgen05) version is a later-round item.
+#include <stdlib.h>
+
 #include "unet_kernels.cuh"
 
 namespace kdip {
@@ -242,6 +244,7 @@ static int set_smem(const void* fn, size_t bytes) {
 int launch_attention_fwd(const bf16* qkv, int N, int T, int heads, int ch, bf16* out, float* lse, cudaStream_t s) {
   KDIP_REQUIRE(ch == CH, KDIP_ESHAPE, "attention: head channels must be 64 (got %d)", ch);
   KDIP_REQUIRE(T % KC == 0, KDIP_ESHAPE, "attention: T=%d must be a multiple of 64", T);
+  if (attention_tc_supported(T, ch)) return launch_attention_fwd_tc(qkv, N, T, heads, out, lse, s);
   const size_t smem = (size_t)(2 * QB + 2 * KC) * LD * sizeof(float);
   static bool once = false;
   if (!once) { int rc = set_smem((const void*)attn_fwd_kernel, smem); if (rc) return rc; once = true; }
@@ -254,6 +257,8 @@ int launch_attention_bwd(const bf16* qkv, const bf16* out, const bf16* d_out, co
                          bf16* dqkv, cudaStream_t s) {
   KDIP_REQUIRE(ch == CH, KDIP_ESHAPE, "attention: head channels must be 64 (got %d)", ch);
   KDIP_REQUIRE(T % KC == 0, KDIP_ESHAPE, "attention: T=%d must be a multiple of 64", T);
+  if (attention_tc_supported(T, ch) && !(getenv("KDIP_ATTN_TC_BWD") && atoi(getenv("KDIP_ATTN_TC_BWD")) == 0))
+    return launch_attention_bwd_tc(qkv, out, d_out, lse, N, T, heads, dqkv, s);
   const size_t smem_q = (size_t)(3 * QB + 2 * KC) * LD * sizeof(float);
   const size_t smem_kv = (size_t)((4 * QB + 2 * KC) * LD + 2 * KC) * sizeof(float);
   static bool once = false;
