@@ -736,10 +736,16 @@ static int build_launch_plan(kdip_unet* u, int N, void* ws, size_t ws_bytes, siz
       K.push_back([=](cudaStream_t s) { return launch_gn_bwd_finalize(red, ab_head, mr_head, nullptr, n, c0, hh * hh, nullptr, 0, 0, kbuf, s); });
       K.push_back([=](cudaStream_t s) { return launch_gn_bwd_apply(hlast.p, c0, nullptr, 0, n, hh, hh, ab_head, kbuf, 1, RS_NONE, g2, nullptr, 0, gin, nullptr, s); });
     }
+    auto sr_two = [](const Rec& r) { return r.kind == 1 && r.r.two; };
+    bool skip_fused = false;   // the gradient `gin` already contains the skip-stack gradient of this block's output
     for (int ri = (int)recs.size() - 1; ri >= 0; --ri) {
       const Rec& rec = recs[ri];
       const BlockDesc& b = u->plan[rec.idx];
-      if (rec.pushes) {
+      // The block input (= previous block's output) may have been pushed on the skip stack: its skip gradient is added by this
+      // block's GroupNorm-backward apply (one more addend) instead of a separate add pass over the tensor.
+      const bf16* in_skip = (ri > 0 && recs[ri - 1].pushes && !sr_two(recs[ri]) && getenv("KDIP_UNFUSED_SKIPADD") == nullptr)
+                                ? hs_grad[recs[ri - 1].push_id] : nullptr;
+      if (rec.pushes && !skip_fused) {
         // this block's output was also consumed through the skip stack: add that gradient
         bf16* gs = hs_grad[rec.push_id];
         Act o = (rec.kind == 1) ? rec.r.out : (rec.kind == 2 ? rec.t.out : rec.in0);
@@ -803,8 +809,9 @@ static int build_launch_plan(kdip_unet* u, int N, void* ws, size_t ws_bytes, siz
         if (!fused1) K.push_back([=](cudaStream_t s) { return launch_gn_bwd_reduce(s0.p, s0.C, s1.p, s1.C, n, Hin, Hin, ab1, 1, rs, g2, red1, s); });
         K.push_back([=](cudaStream_t s) { return launch_gn_bwd_finalize(red1, ab1, mr1, nullptr, n, cin, Hin * Hin, nullptr, 0, 0, kbuf, s); });
         K.push_back([=](cudaStream_t s) {
-          return launch_gn_bwd_apply(s0.p, s0.C, s1.p, s1.C, n, Hin, Hin, ab1, kbuf, 1, rs, g2, extra, extra_mode, dst0, dst1, s);
+          return launch_gn_bwd_apply(s0.p, s0.C, s1.p, s1.C, n, Hin, Hin, ab1, kbuf, 1, rs, g2, extra, extra_mode, dst0, dst1, s, in_skip);
         });
+        skip_fused = in_skip != nullptr;
         std::swap(gin, gfree);
       } else if (rec.kind == 2) {
         const SavedAttn& sa = rec.t;
@@ -832,7 +839,8 @@ static int build_launch_plan(kdip_unet* u, int N, void* ws, size_t ws_bytes, siz
         bf16* dst0 = gfree;
         if (!fuseda) K.push_back([=](cudaStream_t s) { return launch_gn_bwd_reduce(x.p, c, nullptr, 0, n, hh, hh, ab, 0, RS_NONE, g2, red, s); });
         K.push_back([=](cudaStream_t s) { return launch_gn_bwd_finalize(red, ab, mr, nullptr, n, c, T, nullptr, 0, 0, kbuf, s); });
-        K.push_back([=](cudaStream_t s) { return launch_gn_bwd_apply(x.p, c, nullptr, 0, n, hh, hh, ab, kbuf, 0, RS_NONE, g2, gi, 1, dst0, nullptr, s); });
+        K.push_back([=](cudaStream_t s) { return launch_gn_bwd_apply(x.p, c, nullptr, 0, n, hh, hh, ab, kbuf, 0, RS_NONE, g2, gi, 1, dst0, nullptr, s, in_skip); });
+        skip_fused = in_skip != nullptr;
         std::swap(gin, gfree);
       } else {
         // conv_in dgrad: g_h0 -> fp32 NCHW grad wrt the (scaled) UNet input; plan rebuilt lazily on pointer change

@@ -511,7 +511,8 @@ template <int VEC, int RS, bool SILU, int EXTRA>
 __global__ void __launch_bounds__(GN_THREADS, VEC == 4 ? 4 : 2)
     gn_bwd_apply_kernel(const bf16* __restrict__ s0, int C0, const bf16* __restrict__ s1, int C1, int H, int W,
                         const float* __restrict__ ab, const float* __restrict__ k, const bf16* __restrict__ gy,
-                        const bf16* __restrict__ extra, int pix_per_block, bf16* __restrict__ d0, bf16* __restrict__ d1) {
+                        const bf16* __restrict__ extra, int pix_per_block, bf16* __restrict__ d0, bf16* __restrict__ d1,
+                        const bf16* __restrict__ skip_grad) {
   constexpr int U = (RS == RS_NEAREST_UP2 && EXTRA == 2) ? 1 : BwdUnroll<RS>::value;
   const int C = C0 + C1, vec = C / VEC;
   const int rows = GN_THREADS / vec;
@@ -537,6 +538,8 @@ __global__ void __launch_bounds__(GN_THREADS, VEC == 4 ? 4 : 2)
   if (EXTRA == 1) exb = extra + (size_t)n * P * C + c0;
   if (EXTRA == 2) exb = extra + (size_t)n * Pg * C + c0;
   bf16* dst = (c0 < C0) ? d0 + (size_t)n * P * C0 + c0 : d1 + (size_t)n * P * C1 + (c0 - C0);
+  // gradient that reached the (single-source) input through the UNet's skip stack (unet.py:655,662): one more addend
+  const bf16* sgb = (skip_grad != nullptr && c0 < C0) ? skip_grad + (size_t)n * P * C0 + c0 : nullptr;
   const int Cd = (c0 < C0) ? C0 : C1;
   const int p_end = min(P, (int)(blockIdx.x + 1) * pix_per_block);
   int p = blockIdx.x * pix_per_block + row;
@@ -545,6 +548,7 @@ __global__ void __launch_bounds__(GN_THREADS, VEC == 4 ? 4 : 2)
     GTaps<VEC, RS> g;
     Raw<VEC> e1;                 // EXTRA == 1
     GTaps<VEC, RS> e2;           // EXTRA == 2
+    Raw<VEC> sg;                 // skip-stack gradient
   };
   auto load = [&](int pp) {
     Loaded L;
@@ -553,6 +557,7 @@ __global__ void __launch_bounds__(GN_THREADS, VEC == 4 ? 4 : 2)
     L.g = ld_gtaps<VEC, RS>(gyb, y, x, W, C);
     if (EXTRA == 1) L.e1 = ldraw<VEC>(exb + (size_t)pp * C);
     if (EXTRA == 2) L.e2 = ld_gtaps<VEC, RS>(exb, y, x, W, C);
+    if (sgb != nullptr) L.sg = ldraw<VEC>(sgb + (size_t)pp * C0);
     return L;
   };
   auto finish = [&](const Loaded& L, int pp) {
@@ -575,6 +580,12 @@ __global__ void __launch_bounds__(GN_THREADS, VEC == 4 ? 4 : 2)
 #pragma unroll
       for (int j = 0; j < VEC; ++j) r[j] += e[j];
     }
+    if (sgb != nullptr) {
+      float e[VEC];
+      unpackv<VEC>(L.sg, e);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) r[j] += e[j];
+    }
     storev<VEC>(dst + (size_t)pp * Cd, r);
   };
   for (; p + (U - 1) * rows < p_end; p += U * rows) {
@@ -589,9 +600,10 @@ __global__ void __launch_bounds__(GN_THREADS, VEC == 4 ? 4 : 2)
 
 int launch_gn_bwd_apply(const bf16* src0, int C0, const bf16* src1, int C1, int N, int H, int W, const float* ab,
                         const float* k, int act_silu, int resample, const bf16* gy, const bf16* extra, int extra_mode,
-                        bf16* dst0, bf16* dst1, cudaStream_t s) {
+                        bf16* dst0, bf16* dst1, cudaStream_t s, const bf16* skip_grad) {
   const int C = C0 + C1;
   KDIP_REQUIRE(C0 % 8 == 0 && C1 % 8 == 0 && C / 8 <= GN_THREADS && C > 0, KDIP_ESHAPE, "gn_bwd_apply: channels %d+%d unsupported", C0, C1);
+  KDIP_REQUIRE(skip_grad == nullptr || C1 == 0, KDIP_EINVAL, "gn_bwd_apply: skip_grad only for a single-source input");
   KDIP_REQUIRE(extra_mode == 0 || extra != nullptr, KDIP_EINVAL, "gn_bwd_apply: extra_mode set without tensor");
   KDIP_REQUIRE(extra_mode >= 0 && extra_mode <= 2, KDIP_EINVAL, "gn_bwd_apply: bad extra_mode %d", extra_mode);
   const int VEC = bwd_vec(C);
@@ -599,7 +611,7 @@ int launch_gn_bwd_apply(const bf16* src0, int C0, const bf16* src1, int C1, int 
   dim3 grid;
   int ppb;
   gn_grid(N, H * W, rows, &grid, &ppb);
-#define GN_BA(V, RS, SL, EX) gn_bwd_apply_kernel<V, RS, SL, EX><<<grid, GN_THREADS, 0, s>>>(src0, C0, src1, C1, H, W, ab, k, gy, extra, ppb, dst0, dst1)
+#define GN_BA(V, RS, SL, EX) gn_bwd_apply_kernel<V, RS, SL, EX><<<grid, GN_THREADS, 0, s>>>(src0, C0, src1, C1, H, W, ab, k, gy, extra, ppb, dst0, dst1, skip_grad)
 #define GN_BA_V(RS, SL, EX) do { if (VEC == 4) GN_BA(4, RS, SL, EX); else GN_BA(8, RS, SL, EX); } while (0)
 #define GN_BA_EX(RS, SL) do { if (extra_mode == 0) GN_BA_V(RS, SL, 0); else if (extra_mode == 1) GN_BA_V(RS, SL, 1); else GN_BA_V(RS, SL, 2); } while (0)
   if (resample == RS_NONE) { if (act_silu) GN_BA_EX(RS_NONE, true); else GN_BA_EX(RS_NONE, false); }

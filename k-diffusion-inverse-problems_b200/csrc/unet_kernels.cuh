@@ -33,9 +33,10 @@ int launch_gn_bwd_finalize(const float* red, const float* ab, const float* mr, c
                            const float* film, int film_stride, int film_off, float* k, cudaStream_t s);
 // backward, pass 2: g_x = k0*g_u + k1 + k2*x (+ extra) written to dst0 [N,H,W,C0] / dst1 [N,H,W,C1].
 // extra_mode: 0 none, 1 tensor at x's resolution [N,H,W,C0+C1], 2 tensor at g_y's resolution (resample^T applied)
+// skip_grad (single-source inputs only, optional): [N,H,W,C0] gradient that reached x through the skip stack, added as well
 int launch_gn_bwd_apply(const bf16* src0, int C0, const bf16* src1, int C1, int N, int H, int W, const float* ab,
                         const float* k, int act_silu, int resample, const bf16* gy, const bf16* extra, int extra_mode,
-                        bf16* dst0, bf16* dst1, cudaStream_t s);
+                        bf16* dst0, bf16* dst1, cudaStream_t s, const bf16* skip_grad = nullptr);
 
 // y[i] += alpha * x[i]  (fp32, tiny vectors such as biases)
 int launch_axpy_f32(float* y, const float* x, float alpha, int n, cudaStream_t s);
