@@ -79,3 +79,29 @@ def test_ffhq_unet_forward(golden_ffhq):
     e_max, e_l2 = _errs(out, ref)
     print(f"ffhq unet fwd: max-rel {e_max:.3e} l2-rel {e_l2:.3e}")
     assert e_max < 3e-2 and e_l2 < 1.5e-2
+
+
+def test_imagenet_style_unet_forward_vjp():
+    """The ImageNet architecture of configs[3] (2 res-blocks per level, attention at 32x32 / 16x16 / 8x8 = T 1024 / 256 / 64, concatenated
+    inputs up to 8x the base width) at image size 128 and base width 64 so the fp32 CPU oracle runs in seconds: forward and
+    input-VJP against oracle.unet_forward + autograd (guided_diffusion/unet.py:636-668; condition/condition.py:146)."""
+    from oracle import unet_ref
+    from kdip.unet import UNetEngine
+    cfg = unet_ref.UNetConfig(128, 64, 2, "32,16,8")    # attention at 32x32, 16x16, 8x8 tokens (ds 4, 8, 16)
+    sd = unet_ref.init_state_dict(cfg, seed=3)
+    eng = UNetEngine(sd, image_size=128, num_channels=64, num_res_blocks=2, attention_resolutions="32,16,8")
+    x = I.unet_input(128, batch=2, seed=41)
+    t = torch.tensor([11, 640])
+    out = eng.forward(x.cuda(), t.cuda())
+    xr = x.clone().requires_grad_()
+    ref = unet_ref.unet_forward(sd, cfg, xr, t)
+    e_max, e_l2 = _errs(out, ref.detach())
+    print(f"imagenet-style unet fwd: max-rel {e_max:.3e} l2-rel {e_l2:.3e}")
+    assert torch.isfinite(out).all()
+    assert e_max < 3e-2 and e_l2 < 1.5e-2
+    v = I.unet_seed(out.shape, seed=42)
+    (gref,) = torch.autograd.grad(ref, xr, v)
+    gx = eng.vjp(v.cuda())
+    e_max, e_l2 = _errs(gx, gref)
+    print(f"imagenet-style unet vjp: max-rel {e_max:.3e} l2-rel {e_l2:.3e}")
+    assert e_max < 5e-2 and e_l2 < 3e-2
