@@ -9,6 +9,8 @@
 //          solve is rows_r2c -> cols(op) -> rows_c2r = 3 kernels, each streaming the plane once.
 //   rows:  inverse complex-to-real with a fused epilogue  out = alpha * res * mul + beta * add.
 // fp32 radix-2 in shared memory; twiddles from sincospif (exact argument reduction).
+#include <stdlib.h>
+
 #include "kdip_common.cuh"
 #include "fft.cuh"
 
@@ -209,6 +211,7 @@ int check_fft_size(int S, int planes) {
 int launch_rows_r2c(const float* x, float2* out, int planes, int S, cudaStream_t s) {
   int rc = check_fft_size(S, planes);
   if (rc) return rc;
+  if (S == 256 && !getenv("KDIP_FFT_RADIX2")) return launch_rows_r2c_256(x, out, planes, s);
   const int T = rows_T(S, planes);
   const size_t smem = (size_t)(S / 2 + T * (S + 1)) * sizeof(float2);
   rows_r2c_kernel<<<(unsigned)((size_t)planes * S / (2 * T)), FFT_THREADS, smem, s>>>(x, out, S, ilog2(S), T);
@@ -220,6 +223,7 @@ int launch_rows_c2r(const float2* in, float* out, int planes, int S, float alpha
                     cudaStream_t s) {
   int rc = check_fft_size(S, planes);
   if (rc) return rc;
+  if (S == 256 && !getenv("KDIP_FFT_RADIX2")) return launch_rows_c2r_256(in, out, planes, alpha, mul, beta, add, s);
   const int T = rows_T(S, planes);
   const size_t smem = (size_t)(S / 2 + T * (S + 1)) * sizeof(float2);
   rows_c2r_kernel<<<(unsigned)((size_t)planes * S / (2 * T)), FFT_THREADS, smem, s>>>(in, out, S, ilog2(S), T, alpha, mul, beta, add);
@@ -230,6 +234,7 @@ int launch_rows_c2r(const float2* in, float* out, int planes, int S, float alpha
 int launch_cols(const float2* in, float2* out, int planes, int S, const SpecOp& op, cudaStream_t s) {
   int rc = check_fft_size(S, planes);
   if (rc) return rc;
+  if (S == 256 && !getenv("KDIP_FFT_RADIX2")) return launch_cols_256(in, out, planes, op, s);
   const int Sh = S / 2 + 1, groups = (Sh + 7) / 8;
   const size_t smem = (size_t)(S / 2 + 2 * 8 * (S + 1)) * sizeof(float2);
   cols_kernel<<<(unsigned)(planes * groups), FFT_THREADS, smem, s>>>(in, out, S, ilog2(S), op);

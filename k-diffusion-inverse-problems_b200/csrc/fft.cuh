@@ -30,4 +30,9 @@ int launch_rows_c2r(const float2* in, float* out, int planes, int S, float alpha
                     cudaStream_t s);
 int launch_cols(const float2* in, float2* out, int planes, int S, const SpecOp& op, cudaStream_t s);
 
+// S = 256: register radix-16 x 16 transforms (fft256.cu); the launchers above dispatch to them
+int launch_rows_r2c_256(const float* x, float2* out, int planes, cudaStream_t s);
+int launch_rows_c2r_256(const float2* in, float* out, int planes, float alpha, const float* mul, float beta, const float* add, cudaStream_t s);
+int launch_cols_256(const float2* in, float2* out, int planes, const SpecOp& op, cudaStream_t s);
+
 }  // namespace kdip

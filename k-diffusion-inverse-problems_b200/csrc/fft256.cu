@@ -1,0 +1,226 @@
+// 256-point register FFTs for the spectral operators at the path's image size (S = 256): same three passes as fft.cu
+// (rows real->half spectrum, columns forward + pointwise op + inverse, rows half spectrum->real with fused epilogue;
+// condition/measurements.py:139-156,178-196, condition/diffpir_utils/utils_sisr.py:22-41, condition/condition.py:356-357,408-410),
+// but each 256-point transform is 16 x 16: 16 threads hold 16 complex values each, a radix-16 butterfly in registers
+// (two radix-4 layers), the W256 twiddles from a shared-memory table, ONE transposition through shared memory, a second radix-16.
+// The radix-2 shared-memory kernels of fft.cu (8 barrier-separated stages per transform) remain for S < 256.
+#include "kdip_common.cuh"
+#include "fft.cuh"
+
+namespace kdip {
+
+static constexpr int F_THREADS = 256;     // 16 transforms x 16 threads
+static constexpr int F_LD = 17;           // padded row of the per-transform 16 x 16 exchange tile
+static constexpr int F_TILE = 16 * F_LD + 1;   // per-transform stride (odd: spreads the 16 transforms over the banks)
+
+__device__ __forceinline__ float2 c_add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 c_sub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 c_mul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+
+// 4-point DFT in place: forward W4 = -i, inverse W4 = +i
+template <bool INV>
+__device__ __forceinline__ void fft4(float2& a, float2& b, float2& c, float2& d) {
+  const float2 s0 = c_add(a, c), s1 = c_sub(a, c), s2 = c_add(b, d), s3 = c_sub(b, d);
+  const float2 r = INV ? make_float2(-s3.y, s3.x) : make_float2(s3.y, -s3.x);   // -+ i * s3
+  a = c_add(s0, s2);
+  c = c_sub(s0, s2);
+  b = c_add(s1, r);
+  d = c_sub(s1, r);
+}
+
+// 16-point DFT, natural order in and out (n = 4a + b -> k = c + 4d; the register permutation is resolved at compile time)
+template <bool INV>
+__device__ __forceinline__ void fft16(float2 (&v)[16]) {
+  constexpr float C1 = 0.92387953251128674f, S1 = 0.38268343236508977f, C2 = 0.70710678118654752f;
+#pragma unroll
+  for (int b = 0; b < 4; ++b) fft4<INV>(v[b], v[4 + b], v[8 + b], v[12 + b]);
+  // v[4c + b] *= W16^(b c), W16 = exp(-+ 2 pi i / 16)
+  const float sg = INV ? 1.f : -1.f;
+  const float2 w1 = make_float2(C1, sg * S1), w2 = make_float2(C2, sg * C2), w3 = make_float2(S1, sg * C1);
+  const float2 w4 = make_float2(0.f, sg), w6 = make_float2(-C2, sg * C2), w9 = make_float2(-C1, -sg * S1);
+  v[5] = c_mul(v[5], w1); v[6] = c_mul(v[6], w2); v[7] = c_mul(v[7], w3);
+  v[9] = c_mul(v[9], w2); v[10] = c_mul(v[10], w4); v[11] = c_mul(v[11], w6);
+  v[13] = c_mul(v[13], w3); v[14] = c_mul(v[14], w6); v[15] = c_mul(v[15], w9);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) fft4<INV>(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+  // X[c + 4d] sits in v[4c + d]
+  float2 t[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) t[k] = v[4 * (k & 3) + (k >> 2)];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) v[k] = t[k];
+}
+
+// One 256-point transform spread over the 16 threads j = 0..15 of a group.  In: u[n1] = x[16 n1 + j].  Out: u[k2] = X[j + 16 k2].
+// `tile` is this transform's exchange tile; every thread of the CTA must call (two __syncthreads inside).
+template <bool INV>
+__device__ __forceinline__ void fft256(float2 (&u)[16], int j, float2* tile, const float2* tw) {
+  fft16<INV>(u);                       // over n1: u[k1] = Y[k1][n2 = j]
+#pragma unroll
+  for (int k1 = 1; k1 < 16; ++k1) {
+    float2 w = tw[j * k1];             // exp(-2 pi i j k1 / 256)
+    if (INV) w.y = -w.y;
+    u[k1] = c_mul(u[k1], w);
+  }
+  __syncthreads();                     // the tile may still be read by the previous user
+#pragma unroll
+  for (int k1 = 0; k1 < 16; ++k1) tile[k1 * F_LD + j] = u[k1];
+  __syncthreads();
+#pragma unroll
+  for (int n2 = 0; n2 < 16; ++n2) u[n2] = tile[j * F_LD + n2];
+  fft16<INV>(u);                       // over n2: u[k2] = X[j + 16 k2]
+}
+
+__device__ __forceinline__ void make_tw256(float2* tw) {
+  float s, c;
+  sincospif(2.0f * (float)threadIdx.x / 256.f, &s, &c);
+  tw[threadIdx.x] = make_float2(c, -s);
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// rows, real -> half spectrum: 32 real rows (16 packed complex transforms) per CTA
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(F_THREADS) rows_r2c_256_kernel(const float* __restrict__ x, float2* __restrict__ out) {
+  __shared__ float2 tw[256];
+  extern __shared__ float2 tiles[];   // [16][F_TILE]
+  constexpr int S = 256, Sh = 129;
+  make_tw256(tw);
+  const int f = threadIdx.x >> 4, j = threadIdx.x & 15;
+  const size_t row0 = (size_t)blockIdx.x * 32;
+  const float* ra = x + (row0 + 2 * f) * S;
+  const float* rb = ra + S;
+  float2 u[16];
+#pragma unroll
+  for (int n1 = 0; n1 < 16; ++n1) u[n1] = make_float2(__ldg(ra + 16 * n1 + j), __ldg(rb + 16 * n1 + j));
+  float2* tile = tiles + f * F_TILE;
+  fft256<false>(u, j, tile, tw);
+  __syncthreads();
+#pragma unroll
+  for (int k2 = 0; k2 < 16; ++k2) tile[j * F_LD + k2] = u[k2];       // Z[j + 16 k2] at [j][k2]
+  __syncthreads();
+  for (int i = threadIdx.x; i < 16 * Sh; i += F_THREADS) {
+    const int t = i / Sh, k = i - t * Sh;
+    const float2* tl = tiles + t * F_TILE;
+    const int kc = (S - k) & (S - 1);
+    const float2 z = tl[(k & 15) * F_LD + (k >> 4)];
+    float2 zc = tl[(kc & 15) * F_LD + (kc >> 4)];
+    zc.y = -zc.y;
+    // Xa = (Z[k] + conj(Z[S-k]))/2 ; Xb = (Z[k] - conj(Z[S-k]))/(2i)
+    const float2 xa = make_float2(0.5f * (z.x + zc.x), 0.5f * (z.y + zc.y));
+    const float2 d = make_float2(0.5f * (z.x - zc.x), 0.5f * (z.y - zc.y));
+    out[(row0 + 2 * t) * Sh + k] = xa;
+    out[(row0 + 2 * t + 1) * Sh + k] = make_float2(d.y, -d.x);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// rows, half spectrum -> real with the fused epilogue out = alpha * res * (mul ? mul : 1) + beta * (add ? add : 0)
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(F_THREADS) rows_c2r_256_kernel(const float2* __restrict__ in, float* __restrict__ out, float alpha,
+                                                                 const float* __restrict__ mul, float beta,
+                                                                 const float* __restrict__ add) {
+  __shared__ float2 tw[256];
+  extern __shared__ float2 tiles[];
+  constexpr int S = 256, Sh = 129;
+  make_tw256(tw);
+  const size_t row0 = (size_t)blockIdx.x * 32;
+  for (int i = threadIdx.x; i < 16 * S; i += F_THREADS) {
+    const int t = i >> 8, k = i & 255;
+    const float2* pa = in + (row0 + 2 * t) * Sh;
+    const float2* pb = pa + Sh;
+    float2 xa, xb;
+    if (k < Sh) { xa = pa[k]; xb = pb[k]; }
+    else { xa = pa[S - k]; xa.y = -xa.y; xb = pb[S - k]; xb.y = -xb.y; }
+    // Z = Xa + i*Xb, element k = 16 n1 + n2 stored at [n2][n1]
+    tiles[t * F_TILE + (k & 15) * F_LD + (k >> 4)] = make_float2(xa.x - xb.y, xa.y + xb.x);
+  }
+  __syncthreads();
+  const int f = threadIdx.x >> 4, j = threadIdx.x & 15;
+  float2* tile = tiles + f * F_TILE;
+  float2 u[16];
+#pragma unroll
+  for (int n1 = 0; n1 < 16; ++n1) u[n1] = tile[j * F_LD + n1];
+  fft256<true>(u, j, tile, tw);
+  const size_t oa = (row0 + 2 * f) * S, ob = oa + S;
+#pragma unroll
+  for (int k2 = 0; k2 < 16; ++k2) {
+    const int c = j + 16 * k2;
+    float va = alpha * u[k2].x, vb = alpha * u[k2].y;
+    if (mul) { va *= mul[oa + c]; vb *= mul[ob + c]; }
+    if (add) { va += beta * add[oa + c]; vb += beta * add[ob + c]; }
+    out[oa + c] = va;
+    out[ob + c] = vb;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// columns: 16 spectrum columns of one plane per CTA; thread (j, c): column c, member j of that column's 16-thread group
+// (tid = 16 j + c, so that a warp touches two 128-byte row segments of the [ky][kx] arrays)
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(F_THREADS) cols_256_kernel(const float2* __restrict__ in, float2* __restrict__ out, SpecOp op) {
+  __shared__ float2 tw[256];
+  extern __shared__ float2 tiles[];
+  constexpr int S = 256, Sh = 129, G = 9;   // column groups per plane
+  make_tw256(tw);
+  const int p = blockIdx.x / G, kx0 = (blockIdx.x - p * G) * 16;
+  const int j = threadIdx.x >> 4, c = threadIdx.x & 15;
+  const int kx = kx0 + c;
+  const bool live = kx < Sh;
+  const float2* src = in + (size_t)p * S * Sh + kx;
+  float2* tile = tiles + c * F_TILE;
+  float2 u[16];
+#pragma unroll
+  for (int n1 = 0; n1 < 16; ++n1) u[n1] = live ? src[(size_t)(16 * n1 + j) * Sh] : make_float2(0.f, 0.f);
+  fft256<false>(u, j, tile, tw);            // u[k2] = X[ky = j + 16 k2]
+  if (op.mode != SPEC_FORWARD_ONLY) {
+    const int img = p / op.planes_per_image;
+    if (live) {
+#pragma unroll
+      for (int k2 = 0; k2 < 16; ++k2) {
+        const size_t sidx = (size_t)(j + 16 * k2) * Sh + kx;
+        float2 v = u[k2];
+        if (op.mode == SPEC_MULT) {
+          float2 m = op.otf[sidx];
+          if (op.conj_otf) m.y = -m.y;
+          v = c_mul(v, m);
+        } else if (op.mode == SPEC_DIV_CONJ) {
+          const float2 fb = op.otf[sidx];
+          const float den = op.sigma_s2 + op.theta[img] * (fb.x * fb.x + fb.y * fb.y);
+          v = c_mul(make_float2(v.x / den, v.y / den), make_float2(fb.x, -fb.y));
+        } else if (op.mode == SPEC_DIV_TABLE) {
+          const float den = op.sigma_s2 + op.theta[img] * op.table[sidx];
+          v = make_float2(v.x / den, v.y / den);
+        }
+        u[k2] = v;
+      }
+    }
+    // inverse along ky: the value for input index m = 16 k2 + j is already in u[n1 = k2] of thread n2 = j
+    fft256<true>(u, j, tile, tw);
+  }
+  if (live) {
+    float2* dst = out + (size_t)p * S * Sh + kx;
+#pragma unroll
+    for (int k2 = 0; k2 < 16; ++k2) dst[(size_t)(j + 16 * k2) * Sh] = u[k2];
+  }
+}
+
+static constexpr size_t kTilesBytes = (size_t)16 * F_TILE * sizeof(float2);
+
+int launch_rows_r2c_256(const float* x, float2* out, int planes, cudaStream_t s) {
+  rows_r2c_256_kernel<<<(unsigned)((size_t)planes * 256 / 32), F_THREADS, kTilesBytes, s>>>(x, out);
+  KDIP_LAUNCH_CHECK();
+  return KDIP_OK;
+}
+int launch_rows_c2r_256(const float2* in, float* out, int planes, float alpha, const float* mul, float beta, const float* add, cudaStream_t s) {
+  rows_c2r_256_kernel<<<(unsigned)((size_t)planes * 256 / 32), F_THREADS, kTilesBytes, s>>>(in, out, alpha, mul, beta, add);
+  KDIP_LAUNCH_CHECK();
+  return KDIP_OK;
+}
+int launch_cols_256(const float2* in, float2* out, int planes, const SpecOp& op, cudaStream_t s) {
+  cols_256_kernel<<<(unsigned)(planes * 9), F_THREADS, kTilesBytes, s>>>(in, out, op);
+  KDIP_LAUNCH_CHECK();
+  return KDIP_OK;
+}
+
+}  // namespace kdip
