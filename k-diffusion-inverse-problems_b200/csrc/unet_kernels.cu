@@ -731,34 +731,59 @@ int launch_conv_small_cin(const float* in, const float* in_scale, const float* w
 // taps of every pixel become one 64-channel bf16 NHWC row, so the conv runs on the tensor cores as a 1x1 implicit GEMM
 // with K = 64 (csrc/conv_gemm.cu) instead of a CUDA-core direct conv.
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void im2col3x3_kernel(const float* __restrict__ in, const float* __restrict__ in_scale, int CIN, int H, int W,
-                                 bf16* __restrict__ out, size_t total) {
-  // one thread = one pixel x 8 of the 64 im2col channels
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int v = (int)(i & 7);
-    const size_t pix = i >> 3;
+// one thread = one pixel x 8 of the 64 im2col channels; CIN and the octet index are compile-time so that every (tap, channel)
+// pair resolves to constant offsets (the runtime k / CIN of the first version made the kernel 2.5x slower than its stores)
+template <int CIN, int V>
+__device__ __forceinline__ void im2col_octet(const float* __restrict__ img, float sc, int y, int x, int H, int W, bf16* __restrict__ dst) {
+  float f[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int k = V * 8 + j;
+    float val = 0.f;
+    if (k < 9 * CIN) {
+      const int tap = k / CIN, ci = k - tap * CIN;
+      const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) val = __ldg(img + ((size_t)ci * H + yy) * W + xx) * sc;
+    }
+    f[j] = val;
+  }
+  stv(dst + V * 8, pack8(f));
+}
+// 256 pixels per CTA: thread = pixel builds its 128-byte row in shared memory (144-byte pitch: conflict-free 16-byte stores),
+// then the CTA streams the 32 KB tile out with fully coalesced 16-byte stores.
+template <int CIN>
+__global__ void __launch_bounds__(256) im2col3x3_kernel(const float* __restrict__ in, const float* __restrict__ in_scale, int H, int W,
+                                                        bf16* __restrict__ out, size_t total_pix) {
+  __shared__ __align__(16) uint8_t tile[256 * 144];
+  const size_t pix0 = (size_t)blockIdx.x * 256;
+  const size_t pix = pix0 + threadIdx.x;
+  if (pix < total_pix) {
     const int x = (int)(pix % W), y = (int)((pix / W) % H);
     const size_t n = pix / ((size_t)W * H);
     const float sc = in_scale ? __ldg(in_scale + n) : 1.f;
-    float f[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int k = v * 8 + j;
-      float val = 0.f;
-      if (k < 9 * CIN) {
-        const int tap = k / CIN, ci = k - tap * CIN;
-        const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
-        if (yy >= 0 && yy < H && xx >= 0 && xx < W) val = __ldg(in + ((n * CIN + ci) * H + yy) * W + xx) * sc;
-      }
-      f[j] = val;
-    }
-    stv(out + pix * 64 + v * 8, pack8(f));
+    const float* img = in + n * CIN * (size_t)H * W;
+    bf16* dst = reinterpret_cast<bf16*>(tile + threadIdx.x * 144);
+    im2col_octet<CIN, 0>(img, sc, y, x, H, W, dst);
+    im2col_octet<CIN, 1>(img, sc, y, x, H, W, dst);
+    im2col_octet<CIN, 2>(img, sc, y, x, H, W, dst);
+    im2col_octet<CIN, 3>(img, sc, y, x, H, W, dst);
+    im2col_octet<CIN, 4>(img, sc, y, x, H, W, dst);
+    im2col_octet<CIN, 5>(img, sc, y, x, H, W, dst);
+    im2col_octet<CIN, 6>(img, sc, y, x, H, W, dst);
+    im2col_octet<CIN, 7>(img, sc, y, x, H, W, dst);
   }
+  __syncthreads();
+  const size_t npix = total_pix - pix0 < 256 ? total_pix - pix0 : 256;
+  uint4* o = reinterpret_cast<uint4*>(out + pix0 * 64);
+  for (int i = threadIdx.x; i < (int)npix * 8; i += 256)
+    o[i] = *reinterpret_cast<const uint4*>(tile + (i >> 3) * 144 + (i & 7) * 16);
 }
 int launch_im2col3x3(const float* in, const float* in_scale, int N, int CIN, int H, int W, bf16* out, cudaStream_t s) {
-  KDIP_REQUIRE(9 * CIN <= 64, KDIP_ESHAPE, "im2col3x3: 9*CIN=%d exceeds the 64-channel row", 9 * CIN);
-  const size_t total = (size_t)N * H * W * 8;
-  im2col3x3_kernel<<<ew_blocks(total, 256), 256, 0, s>>>(in, in_scale, CIN, H, W, out, total);
+  KDIP_REQUIRE(CIN == 3 || CIN == 6, KDIP_ESHAPE, "im2col3x3: CIN must be 3 or 6 (got %d)", CIN);
+  const size_t total = (size_t)N * H * W;
+  const unsigned blocks = (unsigned)((total + 255) / 256);
+  if (CIN == 3) im2col3x3_kernel<3><<<blocks, 256, 0, s>>>(in, in_scale, H, W, out, total);
+  else im2col3x3_kernel<6><<<blocks, 256, 0, s>>>(in, in_scale, H, W, out, total);
   KDIP_LAUNCH_CHECK();
   return KDIP_OK;
 }
