@@ -174,3 +174,32 @@ class ConditionDenoiserRef:
         else:
             raise ValueError(f"Invalid guidance type: '{self.guidance}'.")
         return hat.clip(-1, 1).detach()
+
+
+class ConditionDenoiserV2Ref(ConditionDenoiserRef):
+    """ConditionOpenAIDenoiserV2 (condition/condition.py:277-300) on OpenAIDenoiserV2.forward(return_variance=True)
+    (k_diffusion/external.py:161-169): continuous timestep, no clamp, x0 = x + c_out * eps, per-pixel variances from the
+    ``out_cov`` 1x1 conv on the pre-head feature (pixel domain ``logvar`` and transform domain ``logvar_ot``)."""
+
+    def __init__(self, sd, cfg, cov_w, cov_b, operator, measurement, guidance, mle_sigma_thres=1.0, ortho_tf_type=None, **kw):
+        super().__init__(sd, cfg, operator, measurement, guidance, mle_sigma_thres=mle_sigma_thres, ortho_tf_type=ortho_tf_type, **kw)
+        self.cov_w, self.cov_b = cov_w, cov_b
+
+    def denoiser(self, x, sigma):
+        """external.py:161-169 with return_variance=True."""
+        c_out, c_in = get_scalings(sigma)
+        out, feat = unet_forward(self.sd, self.cfg, x * c_in, self.sched.sigma_to_t(sigma), return_feature=True)
+        logvar, logvar_ot = torch.nn.functional.conv2d(feat, self.cov_w, self.cov_b).chunk(2, dim=1)
+        return out.chunk(2, dim=1)[0], logvar, logvar_ot
+
+    def uncond_pred(self, x, sigma):
+        """condition.py:287-300."""
+        c_out, _ = get_scalings(sigma)
+        model_output, logvar, logvar_ot = self.denoiser(x, sigma)
+        x0_mean = model_output * c_out + x
+        if sigma < self.thres:
+            x0_var = logvar.exp() * c_out.pow(2)
+            theta0_var = logvar_ot.exp() * c_out.pow(2)
+        else:
+            x0_var = theta0_var = sigma.pow(2) / (1 + sigma.pow(2))
+        return x0_mean, x0_var, theta0_var

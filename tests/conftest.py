@@ -23,3 +23,8 @@ def golden_small():
 @pytest.fixture(scope="session")
 def golden_ffhq():
     return np.load(os.path.join(ROOT, "tests", "golden", "golden_ffhq.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_v2():
+    return np.load(os.path.join(ROOT, "tests", "golden", "golden_v2.npz"))

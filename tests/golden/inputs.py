@@ -65,3 +65,18 @@ def theta_map(size, seed=5):
 def sub(a):
     """4x4 spatial subsample used for the 256x256 golden outputs (arrays whose last dim is 256 only)."""
     return a[..., ::4, ::4] if a.shape[-1] == 256 else a
+
+
+# ---- v2 (DWT-Var) denoiser path: 64x64 UNet of width 128 (the reference hard-codes out_cov = Conv2d(128, 6, 1)) ----
+V2_SIGMAS = [0.5, 2.0]     # below / above mle_sigma_thres = 1.0 (sample_condition_openai_v2.py default)
+
+
+def v2_config():
+    from oracle import unet_ref
+    return unet_ref.UNetConfig(64, 128, 1, "16,8")
+
+
+def v2_out_cov(seed=9):
+    """Random-init out_cov head (k_diffusion/external.py:141): weight [6,128,1,1], bias [6]."""
+    g = _g(seed)
+    return torch.randn(6, 128, 1, 1, generator=g) * 0.05, torch.randn(6, generator=g) * 0.5 - 1.0

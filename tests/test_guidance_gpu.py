@@ -210,3 +210,45 @@ def test_unet_module_autograd(tiny_model, golden_small):
     assert errs(pm["variance"], golden_small["pmv.variance"])[1] < 3e-2
     (g2,) = torch.autograd.grad(pm["pred_xstart"].sum(), xs)
     assert torch.isfinite(g2).all() and g2.abs().max() > 0
+
+
+@pytest.mark.parametrize("ot", ["dwt", "dct"])
+@pytest.mark.parametrize("sigma", I.V2_SIGMAS)
+def test_v2_denoiser_type_II_guidance(ot, sigma, golden_v2):
+    """BASELINE configs[4]: ConditionOpenAIDenoiserV2 on OpenAIDenoiserV2 (out_cov head fused into the UNet engine, continuous t,
+    no clamp), type-II guidance x0 + W(theta * W^T v) with the per-pixel transform-domain variance below mle_sigma_thres = 1.0
+    (batched on-device CG) and the closed form above it - vs the reference's own output (golden_v2)."""
+    from condition.condition import ConditionOpenAIDenoiserV2
+    from guided_diffusion.script_util import create_gaussian_diffusion
+    from guided_diffusion.unet import UNetModel
+    from k_diffusion.external import OpenAIDenoiserV2
+    from oracle import unet_ref
+    cfg = I.v2_config()
+    sd = unet_ref.init_state_dict(cfg, seed=0)
+    model = UNetModel(image_size=64, in_channels=3, model_channels=128, out_channels=6, num_res_blocks=1,
+                      attention_resolutions=cfg.attention_ds(), channel_mult=cfg.resolved_channel_mult(), num_head_channels=64,
+                      use_scale_shift_norm=True, resblock_updown=True)
+    model.load_state_dict(sd, strict=True)
+    model = model.eval().cuda()
+    diffusion = create_gaussian_diffusion(learn_sigma=True)
+    den = OpenAIDenoiserV2(model, diffusion, device="cuda", ortho_tf_type=ot).cuda()
+    cov_w, cov_b = I.v2_out_cov(seed=9)
+    with torch.no_grad():
+        den.out_cov.weight.copy_(cov_w)
+        den.out_cov.bias.copy_(cov_b)
+    op = make_op("gaussian_blur", 64)
+    y = torch.from_numpy(golden_v2["v2.y"]).cuda()
+    cm = ConditionOpenAIDenoiserV2(denoiser=den, operator=op, measurement=(y, y.reshape(1, -1)), guidance="II", device="cuda",
+                                   mle_sigma_thres=1.0, ortho_tf_type=ot).eval()
+    xt = I.xt(64, sigma, seed=21).cuda()
+    hat = cm(xt, torch.tensor([sigma]).cuda())
+    assert torch.isfinite(hat).all()
+    e_max, e_l2 = errs(hat, golden_v2[f"v2.{ot}.{sigma}.hat"])
+    print(f"v2 type-II {ot} sigma={sigma}: max {e_max:.3e} l2 {e_l2:.3e}")
+    assert e_max < 6e-2 and e_l2 < 3e-2      # one bf16 UNet forward, no VJP: the floor of the module docstring
+    # batch of 2 identical problems == the single problem
+    y2 = y.expand(2, -1, -1, -1).contiguous()
+    cm2 = ConditionOpenAIDenoiserV2(denoiser=den, operator=op, measurement=(y2, y2.reshape(2, -1)), guidance="II", device="cuda",
+                                    mle_sigma_thres=1.0, ortho_tf_type=ot).eval()
+    hat2 = cm2(xt.expand(2, -1, -1, -1).contiguous(), torch.full((2,), sigma).cuda())
+    assert errs(hat2[1:2], hat)[1] < 1e-2
