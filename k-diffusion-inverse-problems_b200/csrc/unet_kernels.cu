@@ -3,6 +3,8 @@
 //   GroupNorm backward (reduce / finalize / apply)                                           autograd of the above
 //   direct 3x3 conv for 3- and 6-channel inputs (first layer, head input-gradient)           unet.py:484,617
 //   timestep embedding + all emb_layers projections                                          nn.py:103-121, unet.py:199-205,473-477
+#include <stdlib.h>
+
 #include "unet_kernels.cuh"
 
 namespace kdip {
@@ -257,7 +259,8 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const bf16* __rest
 
 // grid.x so that ~8 CTAs per SM are resident across the batch; every CTA gets a contiguous pixel range of one image
 static inline void gn_grid(int N, int P, int rows, dim3* grid, int* pix_per_block) {
-  int bx = (num_sms() * 8 + N - 1) / N;
+  static int ctas_per_sm = getenv("KDIP_GN_CTAS") ? atoi(getenv("KDIP_GN_CTAS")) : 8;
+  int bx = (num_sms() * ctas_per_sm + N - 1) / N;
   int ppb = (P + bx - 1) / bx;
   const int quantum = rows * GN_UNROLL;
   ppb = ((ppb + quantum - 1) / quantum) * quantum;
