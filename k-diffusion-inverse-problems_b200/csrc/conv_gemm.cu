@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     // ===================== TMA producer =====================
     if (kHalo) {
       // activation rows: per (segment, 64-channel chunk) the rows y0-1 .. y0+2 (3x3) or y0, y0+1 (1x1) of the work item
-      if (lane == 0 && !(p.dbg & 1)) {
+      if (!(p.dbg & 1)) {
         int slot = 0;
         uint32_t ph = 0;
         for (int work = work0; work < p.total_work; work += work_stride) {
@@ -215,7 +215,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             for (int ch = 0; ch < p.seg_chunks[s]; ++ch) {
               for (int r = 0; r < nrows; ++r) {
                 mbar_wait(&a_empty_bar[slot], ph ^ 1);
-                if (kPair) {
+                if (!elect_one_sync()) {
+                } else if (kPair) {
                   const uint32_t fb = leader_addr(&a_full_bar[slot]);
                   mbar_arrive_expect_tx_cluster(fb, (uint32_t)kHaloRowBytes);
                   tma_load_4d_2sm(smem + slot * kHaloSlot, &p.mapA[s], fb, ch * kBlockK, t.x0 - 1, ybase + r, t.n0);
@@ -223,13 +224,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                   mbar_arrive_expect_tx(&a_full_bar[slot], (uint32_t)kHaloRowBytes);
                   tma_load_4d(smem + slot * kHaloSlot, &p.mapA[s], &a_full_bar[slot], ch * kBlockK, t.x0 - 1, ybase + r, t.n0);
                 }
+                __syncwarp();
                 if (++slot == kHaloSlots) { slot = 0; ph ^= 1; }
               }
             }
           }
         }
       }
-    } else if (lane == 0) {
+    } else {
+      // the whole warp walks the loop (converged); one elected lane issues the TMA instructions
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t tx_bytes = (uint32_t)stage_bytes;
@@ -245,7 +248,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
               mbar_wait(&empty_bar[stage], phase ^ 1);
               uint8_t* a_dst = smem + stage * stage_bytes;
               uint8_t* b_dst = a_dst + a_bytes;
-              if (kPair) {
+              if (!elect_one_sync()) {
+                // not the issuing lane
+              } else if (kPair) {
                 // this CTA's pixel tile + its half of the weight rows; completion is counted on the LEADER's barrier
                 const uint32_t fb = leader_addr(&full_bar[stage]);
                 mbar_arrive_expect_tx_cluster(fb, tx_bytes);
@@ -258,6 +263,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                 if (mt == 2) tma_load_4d(a_dst + kABytes, &p.mapA[s], &full_bar[stage], ch * kBlockK, t1.x0 + dx, t1.y0 + dy, t1.n0);
                 tma_load_2d(b_dst, &p.mapB[s], &full_bar[stage], ch * kBlockK, tap * p.Cout_pad + t.nn0);
               }
+              __syncwarp();
               if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
             }
           }
@@ -267,7 +273,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   } else if (warp == 1) {
     // ===================== MMA issuer (single thread) =====================
     if (kHalo) {
-      if (lane == 0 && rank == 0) {
+      if (rank == 0) {     // converged warp, elected lane issues MMAs and commits
         int aslot = 0, bst = 0, acc = 0;
         uint32_t aph = 0, bph = 0, acc_phase = 0;
         const uint32_t a_base = smem_u32(smem), b_base = smem_u32(b_ring);
@@ -304,43 +310,54 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                   const uint64_t a0_desc = umma_desc_sw128_bo(a_base + rs[dyi] * kHaloSlot + roff * 128u, bo);
                   const uint64_t a1_desc = umma_desc_sw128_bo(a_base + rs[dyi + 1] * kHaloSlot + roff * 128u, bo);
                   const uint64_t b_desc = umma_desc_sw128(b_base + bst * b_stage_bytes);
+                  if (elect_one_sync()) {
 #pragma unroll
                   for (int k = 0; k < kBlockK / 16; ++k) {
+                    const uint32_t acc_k = (accum | (uint32_t)k) ? 1u : 0u;    // only the very first MMA of a work item overwrites
                     if (kPair) {
-                      umma_bf16_ss_2sm(d0, a0_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), p.idesc, accum);
-                      umma_bf16_ss_2sm(d1, a1_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), p.idesc, accum);
+                      umma_bf16_ss_2sm(d0, a0_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), p.idesc, acc_k);
+                      umma_bf16_ss_2sm(d1, a1_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), p.idesc, acc_k);
                     } else if (p.ws) {
-                      umma_bf16_ss_ws_fill(d0, a0_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), p.idesc, accum);
-                      umma_bf16_ss_ws_lastuse(d1, a1_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), p.idesc, accum);
+                      umma_bf16_ss_ws_fill(d0, a0_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), p.idesc, acc_k);
+                      umma_bf16_ss_ws_lastuse(d1, a1_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), p.idesc, acc_k);
                     } else {
-                      umma_bf16_ss(d0, a0_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), p.idesc, accum);
-                      umma_bf16_ss(d1, a1_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), p.idesc, accum);
+                      umma_bf16_ss(d0, a0_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), p.idesc, acc_k);
+                      umma_bf16_ss(d1, a1_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), p.idesc, acc_k);
                     }
-                    accum = 1;
                   }
                   commit(&empty_bar[bst]);
+                  }
+                  __syncwarp();
+                  accum = 1;
                   if (++bst == p.num_stages) { bst = 0; bph ^= 1; }
                 }
                 // rows that no later tap of this chunk reads go back to the producer once the MMAs above retire
-                if (!k3) { commit(&a_empty_bar[rs[0]]); commit(&a_empty_bar[rs[1]]); }
-                else if (dyi < 2) commit(&a_empty_bar[rs[dyi]]);
-                else { commit(&a_empty_bar[rs[2]]); commit(&a_empty_bar[rs[3]]); }
+                if (elect_one_sync()) {
+                  if (!k3) { commit(&a_empty_bar[rs[0]]); commit(&a_empty_bar[rs[1]]); }
+                  else if (dyi < 2) commit(&a_empty_bar[rs[dyi]]);
+                  else { commit(&a_empty_bar[rs[2]]); commit(&a_empty_bar[rs[3]]); }
+                }
+                __syncwarp();
               }
             }
           }
-          commit(&tmem_full_bar[acc]);
+          if (elect_one_sync()) commit(&tmem_full_bar[acc]);
+          __syncwarp();
           if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
       }
-    } else if (lane == 0 && rank == 0) {
+    } else if (rank == 0) {
+      // converged warp; the elected lane issues the MMAs and their commits (tcgen05.commit tracks the issuing thread)
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      const uint32_t bn = (uint32_t)p.BN, idesc = p.idesc;
+      const bool ws = p.ws != 0;
       for (int work = work0; work < p.total_work; work += work_stride) {
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * mt * p.BN);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * mt) * bn;
         for (int kb = 0; kb < kblocks_total; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -348,32 +365,39 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           const uint64_t a_desc = umma_desc_sw128(a_addr);
           const uint64_t a1_desc = umma_desc_sw128(a_addr + kABytes);
           const uint64_t b_desc = umma_desc_sw128(a_addr + a_bytes);
+          if (elect_one_sync()) {
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
             // advance 16 bf16 = 32 bytes inside the 128B swizzle atom: +2 in the (addr>>4) field
+            const uint32_t accum = (kb | k) ? 1u : 0u;
             if (kPair) {
-              umma_bf16_ss_2sm(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), p.idesc, (kb | k) ? 1u : 0u);
-              if (mt == 2) umma_bf16_ss_2sm(d_tmem + (uint32_t)p.BN, a1_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), p.idesc, (kb | k) ? 1u : 0u);
-            } else if (mt == 2 && p.ws) {
-              umma_bf16_ss_ws_fill(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), p.idesc, (kb | k) ? 1u : 0u);
-              umma_bf16_ss_ws_lastuse(d_tmem + (uint32_t)p.BN, a1_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), p.idesc, (kb | k) ? 1u : 0u);
+              umma_bf16_ss_2sm(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, accum);
+              if (mt == 2) umma_bf16_ss_2sm(d_tmem + bn, a1_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, accum);
+            } else if (mt == 2 && ws) {
+              umma_bf16_ss_ws_fill(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, accum);
+              umma_bf16_ss_ws_lastuse(d_tmem + bn, a1_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, accum);
             } else {
-              umma_bf16_ss(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), p.idesc, (kb | k) ? 1u : 0u);
-              if (mt == 2) umma_bf16_ss(d_tmem + (uint32_t)p.BN, a1_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), p.idesc, (kb | k) ? 1u : 0u);
+              umma_bf16_ss(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, accum);
+              if (mt == 2) umma_bf16_ss(d_tmem + bn, a1_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, accum);
             }
           }
           // frees the smem stage (in both CTAs of a pair) when these MMAs retire
           if (kPair) umma_commit_2sm(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
+          }
+          __syncwarp();
           if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
         }
         // accumulator complete -> epilogue (of both CTAs)
-        if (kPair) umma_commit_2sm(&tmem_full_bar[acc]); else umma_commit(&tmem_full_bar[acc]);
+        if (elect_one_sync()) {
+          if (kPair) umma_commit_2sm(&tmem_full_bar[acc]); else umma_commit(&tmem_full_bar[acc]);
+        }
+        __syncwarp();
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else if (warp == 2) {
     // ===================== halo mode: weight producer, one (chunk, tap) slab of BN x 64 per stage =====================
-    if (kHalo && lane == 0 && !(p.dbg & 1)) {
+    if (kHalo && !(p.dbg & 1)) {
       int st = 0;
       uint32_t ph = 0;
       for (int work = work0; work < p.total_work; work += work_stride) {
@@ -382,7 +406,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           for (int ch = 0; ch < p.seg_chunks[s]; ++ch) {
             for (int tap = 0; tap < p.seg_taps[s]; ++tap) {
               mbar_wait(&empty_bar[st], ph ^ 1);
-              if (kPair) {   // this CTA's half of the weight rows
+              if (!elect_one_sync()) {
+              } else if (kPair) {   // this CTA's half of the weight rows
                 const uint32_t fb = leader_addr(&full_bar[st]);
                 mbar_arrive_expect_tx_cluster(fb, (uint32_t)b_stage_bytes);
                 tma_load_2d_2sm(b_ring + st * b_stage_bytes, &p.mapB[s], fb, ch * kBlockK, tap * p.Cout_pad + t.nn0 + rank * p.b_rows);
@@ -390,6 +415,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                 mbar_arrive_expect_tx(&full_bar[st], (uint32_t)b_stage_bytes);
                 tma_load_2d(b_ring + st * b_stage_bytes, &p.mapB[s], &full_bar[st], ch * kBlockK, tap * p.Cout_pad + t.nn0);
               }
+              __syncwarp();
               if (++st == p.num_stages) { st = 0; ph ^= 1; }
             }
           }
@@ -398,7 +424,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     }
   } else if (warp == 3) {
     // ===================== residual producer: TMA-loads the identity-skip tile of every output tile =====================
-    if (lane == 0 && p.res_tma && !(p.dbg & 2)) {
+    if (p.res_tma && !(p.dbg & 2)) {     // converged warp, elected lane issues
       const int n_slabs = p.BN / 64;
       // nearest-up skip (unet.py:107,190-197): the 128-pixel output tile reads a (TH/2 x TW/2) box of the half-resolution source
       const int up = p.res_mode == 3 ? 1 : 0;
@@ -410,13 +436,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           for (int s0 = 0; s0 < n_slabs; s0 += 2, ++it) {
             const int ns = (n_slabs - s0) < 2 ? (n_slabs - s0) : 2;
             mbar_wait(res_empty_bar, (it & 1) ^ 1);
-            mbar_arrive_expect_tx(res_full_bar, (uint32_t)ns * slab_bytes);
-            for (int jj = 0; jj < ns; ++jj) {
-              int c_off = t.nn0 + (s0 + jj) * 64;
-              const CUtensorMap* mp = &p.mapRes;
-              if (p.gn_red != nullptr && c_off >= p.gn_C0) { c_off -= p.gn_C0; mp = &p.mapRes2; }
-              tma_load_4d(res_stage + jj * kSlabBytes, mp, res_full_bar, c_off, t.x0 >> up, t.y0 >> up, t.n0);
+            if (elect_one_sync()) {
+              mbar_arrive_expect_tx(res_full_bar, (uint32_t)ns * slab_bytes);
+              for (int jj = 0; jj < ns; ++jj) {
+                int c_off = t.nn0 + (s0 + jj) * 64;
+                const CUtensorMap* mp = &p.mapRes;
+                if (p.gn_red != nullptr && c_off >= p.gn_C0) { c_off -= p.gn_C0; mp = &p.mapRes2; }
+                tma_load_4d(res_stage + jj * kSlabBytes, mp, res_full_bar, c_off, t.x0 >> up, t.y0 >> up, t.n0);
+              }
             }
+            __syncwarp();
           }
         }
       }

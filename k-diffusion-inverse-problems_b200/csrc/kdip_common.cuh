@@ -78,6 +78,22 @@ __device__ __forceinline__ float dsilu_fast(float u) {
   const float s = fmaf(0.5f, fast_tanh(0.5f * u), 0.5f);
   return s * fmaf(u, 1.f - s, 1.f);
 }
+// One lane of a CONVERGED warp (elect.sync): single-thread issue of TMA / tcgen05 instructions inside warp-uniform control flow.
+// A role written as `if (lane == 0) { loop }` instead makes ptxas wrap every uniform-datapath instruction (UTCHMMA, UTMALDG) in an
+// ELECT / PLOP3 / BRA.U.ANY convergence loop: 136 SASS instructions per k-block in the MMA issuer, which then paced the conv.
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .b32 rx;\n"
+      ".reg .pred px;\n"
+      "elect.sync rx|px, 0xffffffff;\n"
+      "selp.b32 %0, 1, 0, px;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- mbarrier ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

@@ -1,0 +1,31 @@
+"""ImageNet 256x256 ADM UNet (configs[3]: 256 channels, 2 res-blocks, attention at 32/16/8) forward + VJP timing. Usage: [B] [iters]"""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "k-diffusion-inverse-problems_b200")]
+import torch
+from oracle import unet_ref
+from kdip.unet import UNetEngine
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+iters = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+cfg = unet_ref.imagenet_config()
+sd = unet_ref.init_state_dict(cfg, seed=0)
+print("params M", sum(v.numel() for v in sd.values()) / 1e6, "GF fwd/img", unet_ref.unet_flops(cfg) / 1e9, flush=True)
+eng = UNetEngine(sd, image_size=256, num_channels=256, num_res_blocks=2, attention_resolutions="32,16,8")
+print("workspace GB", eng.workspace_bytes(B) / 1e9, flush=True)
+x = torch.randn(B, 3, 256, 256, device="cuda"); t = torch.full((B,), 500.0, device="cuda"); seed = torch.randn(B, 6, 256, 256, device="cuda")
+out = torch.empty(B, 6, 256, 256, device="cuda"); g = torch.empty(B, 3, 256, 256, device="cuda")
+for _ in range(2):
+    eng.forward(x, t, out=out); eng.vjp(seed, out=g)
+torch.cuda.synchronize()
+assert torch.isfinite(out).all() and torch.isfinite(g).all()
+e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+tf = tb = 0.0
+for _ in range(iters):
+    e[0].record(); eng.forward(x, t, out=out); e[1].record(); eng.vjp(seed, out=g); e[2].record()
+    torch.cuda.synchronize()
+    tf += e[0].elapsed_time(e[1]); tb += e[1].elapsed_time(e[2])
+tf /= iters; tb /= iters
+fl = unet_ref.unet_flops(cfg) * B
+print(f"ImageNet UNet B={B}: fwd {tf:.2f} ms ({fl/tf/1e9:.1f} TF/s)  vjp {tb:.2f} ms ({fl/tb/1e9:.1f} TF/s)")
+pr = eng.profile(x, t, seed)
+print("profile: total %.1f ms conv %.1f ms (%.0f TF/s) other %.1f ms" % (pr["total_ms"], pr["conv_ms"], pr["conv_flops"] / pr["conv_ms"] / 1e9, pr["other_ms"]))
