@@ -848,11 +848,11 @@ int conv_plan_build(const kdip_conv_desc* d, ConvPlan* plan) {
   // halo pipeline: a 3x3 first segment on an image at least 128 pixels wide, bf16 NHWC output in 64-channel slabs
   p.halo = (d->seg[0].taps == 9 && d->W % 128 == 0 && d->H % 2 == 0 && d->out_mode == 0 && d->Cout == d->Cout_pad && d->Cout % 64 == 0 &&
             d->res_mode != 2) ? 1 : 0;
-  // Measured on B200 (tools/time_unet.py 32 80, i.e. seconds of back-to-back evaluations under the 1 kW power cap): the halo
-  // pipeline cuts the L2->SM operand traffic by 2.3x and wins 10 % per conv on a cool GPU (558 vs 614 us, 128->128 @ 256^2) but
-  // loses 2-3 % of the whole UNet evaluation in the power-capped steady state the sampler runs in (48.0 vs 47.4 ms).  It stays
-  // opt-in (KDIP_CONV_HALO=1) and under test; the default is the 8x16-tile pipeline with two tiles per work item.
-  if (!(getenv("KDIP_CONV_HALO") && atoi(getenv("KDIP_CONV_HALO")) == 1)) p.halo = 0;
+  // Measured on B200 under sustained load (tools/time_unet.py 32 50), AFTER the issue loops became converged-warp + elect.sync:
+  // 8x16 tiles 41.0 ms per UNet evaluation, halo pipeline 40.7 ms, halo pipeline as CTA pairs 38.1 ms.  (With the old lane-0 issue
+  // loops, which paced every variant at ~1000 clk per k-block, the same A/B read 47.4 / 48.0 / 49.0 ms and the halo was opt-in.)
+  // KDIP_CONV_HALO=0 selects the 8x16-tile pipeline everywhere.
+  if (getenv("KDIP_CONV_HALO") && atoi(getenv("KDIP_CONV_HALO")) == 0) p.halo = 0;
   if (const char* e = getenv("KDIP_CONV_TMAEPI")) { if (atoi(e) == 0) p.halo = 0; }
   // Measured on B200 (tools/halo_probe.py): the 128B swizzle of tcgen05.mma operands is a function of the ABSOLUTE shared-memory
   // address, so a descriptor may start any number of 128-byte rows into a 1024-byte atom with base offset 0; setting the
@@ -913,19 +913,16 @@ int conv_plan_build(const kdip_conv_desc* d, ConvPlan* plan) {
     if (atoi(e) == 1) p.mt = 1;
     if (atoi(e) == 2 && p.tma_epilogue && BN <= 128 && m_tiles % 2 == 0) p.mt = 2;
   }
-  // mt = 2 as CTA pairs (four pixel tiles per work item) measured no faster than single CTAs (B200, 128->128 @ 256^2: 613 vs
-  // 585 us): off unless KDIP_CONV_PAIRMT=1 (kept for the parity tests and future tuning)
-  if (p.mt == 2 && (m_tiles % 4 != 0 || !(getenv("KDIP_CONV_PAIRMT") && atoi(getenv("KDIP_CONV_PAIRMT")) == 1))) p.pair = 0;
+  // mt = 2 as CTA pairs (four pixel tiles per work item): 40.3 vs 41.0 ms per UNet evaluation (sustained); KDIP_CONV_PAIRMT=0: single CTAs
+  if (p.mt == 2 && (m_tiles % 4 != 0 || (getenv("KDIP_CONV_PAIRMT") && atoi(getenv("KDIP_CONV_PAIRMT")) == 0))) p.pair = 0;
   if (p.halo) {
     KDIP_REQUIRE(p.tma_epilogue, KDIP_EINVAL, "conv: internal error, halo pipeline without the TMA epilogue");
     // CTA pairs (M = 256 MMAs, weight rows split across the two CTAs) keep the per-SM shared-memory traffic of the N = 128 MMAs
     // under 128 B/clk: operand reads 96 B/clk + TMA writes ~30 B/clk, against 128 + 46 for single CTAs (measured bound ~75 %)
-    // ... in theory.  Measured (B200, 128->128 @ 256^2, B=32): pairs 588 us vs single CTAs 557 us, and even with operand loads
-    // and epilogue switched off (KDIP_CONV_DBG=3) the M=256 x N=128 pair MMAs issue at 1513 TF/s against 1745 for M=128 x N=128:
-    // single CTAs are the default, KDIP_HALO_PAIR=1 selects pairs (kept under test).
+    // Measured (sustained, whole UNet): pairs 38.1 ms vs single CTAs 40.7 ms.  KDIP_HALO_PAIR=0 selects single CTAs.
     p.mt = 2;
-    p.pair = 0;
-    if (const char* e = getenv("KDIP_HALO_PAIR")) { if (atoi(e) == 1 && m_tiles % 4 == 0) p.pair = 1; }
+    p.pair = (m_tiles % 4 == 0) ? 1 : 0;
+    if (const char* e = getenv("KDIP_HALO_PAIR")) { if (atoi(e) == 0) p.pair = 0; }
   }
   p.b_rows = p.pair ? BN / 2 : BN;
   p.total_work = (m_tiles / (p.mt * (p.pair ? 2 : 1))) * p.n_tiles;

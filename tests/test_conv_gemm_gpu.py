@@ -243,16 +243,16 @@ def test_conv_halo_pipeline(case, pair, monkeypatch):
 
 
 def test_conv_halo_matches_tile_pipeline():
-    """Same conv through the 8x16-tile pipeline and (KDIP_CONV_HALO=1) the halo pipeline: identical up to fp32 summation order."""
+    """Same conv through the halo pipeline (default) and (KDIP_CONV_HALO=0) the 8x16-tile pipeline: identical up to fp32 summation order."""
     import os
     from gpu_util import pack_weight, run_conv, to_nchw_f32, to_nhwc_bf16, relerr
     N, H, W, Ci, Co = 2, 16, 256, 128, 128
     x, w = _mk(N, Ci, H, W, 1), _mk(Co, Ci, 3, 3, 2) / (Ci * 9) ** 0.5
     xa, wp = to_nhwc_bf16(x), pack_weight(w)[0]
-    b = to_nchw_f32(run_conv([(xa, wp, 9)], N, H, W, Co))
-    os.environ["KDIP_CONV_HALO"] = "1"
+    a = to_nchw_f32(run_conv([(xa, wp, 9)], N, H, W, Co))          # default: halo pipeline
+    os.environ["KDIP_CONV_HALO"] = "0"
     try:
-        a = to_nchw_f32(run_conv([(xa, wp, 9)], N, H, W, Co))
+        b = to_nchw_f32(run_conv([(xa, wp, 9)], N, H, W, Co))      # 8x16-tile pipeline
     finally:
         del os.environ["KDIP_CONV_HALO"]
     assert relerr(a, b) < 1.0 / 256
