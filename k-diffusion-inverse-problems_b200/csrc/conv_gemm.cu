@@ -493,7 +493,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           else mbar_arrive(&tmem_empty_bar[acc]);
         }
         // the staging tile (and bias_s) may be rewritten once the previous TMA store has finished reading it
-        if (epi_tid == 0) tma_store_wait_read();
+        // TMA stores are issued (and their bulk groups waited on) by one elected lane of the first epilogue warp, from converged code
+        if (warp == 4) {
+          if (elect_one_sync()) tma_store_wait_read();
+          __syncwarp();
+        }
         if (p.bias != nullptr && epi_tid < 128 && s0 * 64 + epi_tid < p.BN) bias_s[epi_tid] = __ldg(p.bias + t.nn0 + s0 * 64 + epi_tid);
         named_bar_sync(1, kEpiThreads);
         if (p.res_tma) {
@@ -603,17 +607,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             }
           }
         }
-        if (epi_tid == 0) {
-          const int ns = (n_slabs - s0) < 2 ? (n_slabs - s0) : 2;
-          for (int j = 0; j < ns; ++j)
-            tma_store_4d(staging + j * kSlabBytes, &p.mapOut, t.nn0 + (s0 + j) * 64, t.x0, t.y0, t.n0);
-          tma_store_commit();
+        if (warp == 4) {
+          if (elect_one_sync()) {
+            const int ns = (n_slabs - s0) < 2 ? (n_slabs - s0) : 2;
+            for (int j = 0; j < ns; ++j)
+              tma_store_4d(staging + j * kSlabBytes, &p.mapOut, t.nn0 + (s0 + j) * 64, t.x0, t.y0, t.n0);
+            tma_store_commit();
+          }
+          __syncwarp();
         }
       }
      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    if (epi_tid == 0) tma_store_wait_all();
+    if (warp == 4) {
+      if (elect_one_sync()) tma_store_wait_all();
+      __syncwarp();
+    }
   } else if (warp >= 4 && warp < 8) {
     // ===================== legacy epilogue: 4 warps, warp q owns TMEM lanes [32q, 32q+32) =====================
     const int q = warp & 3;
