@@ -882,6 +882,19 @@ int conv_plan_build(const kdip_conv_desc* d, ConvPlan* plan) {
   p.tiles_n = (d->N + p.TN - 1) / p.TN;
   const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
   BN = p.halo ? (d->Cout_pad % 128 == 0 ? 128 : 64) : pick_bn(d->Cout_pad, m_tiles);   // halo: two accumulators per buffer, BN <= 128
+  // 8x16-tile pipeline: N tile 128 with two pixel tiles per work item as CTA pairs ("128p1m2") measured best or tied on every
+  // narrow-level shape with at least ~32 pair work items (tools/gpu_round38.sh sweep, B=32: 16^2 512->512 46.7 -> 34.9 us,
+  // 16^2 1024->512 80.2 -> 56.3, 64^2 128->128 48.1 -> 38.8, 32^2 768->256 95.6 -> 82.2); the 8^2 level keeps N tile 64 pairs.
+  bool force_p1m2 = false;
+  if (!p.halo && d->Cout_pad % 128 == 0 && m_tiles % 4 == 0 && (long)(m_tiles / 4) * (d->Cout_pad / 128) >= 32 && d->out_mode == 0 &&
+      !getenv("KDIP_CONV_BN") && !getenv("KDIP_CONV_MT") && !getenv("KDIP_CONV_PAIR") && !getenv("KDIP_CONV_PAIRMT")) {
+    BN = 128;
+    force_p1m2 = true;
+  }
+  if (const char* e = getenv("KDIP_CONV_BN")) {   // tuning override for the 8x16-tile pipeline
+    const int v = atoi(e);
+    if (!p.halo && (v == 64 || v == 128 || v == 256) && d->Cout_pad % v == 0) BN = v;
+  }
   KDIP_REQUIRE(BN > 0, KDIP_ESHAPE, "conv: Cout_pad=%d unsupported (need 16, 32 or a multiple of 64)", d->Cout_pad);
   p.BN = BN;
   p.n_tiles = d->Cout_pad / BN;
@@ -925,6 +938,7 @@ int conv_plan_build(const kdip_conv_desc* d, ConvPlan* plan) {
   }
   // mt = 2 as CTA pairs (four pixel tiles per work item): 40.3 vs 41.0 ms per UNet evaluation (sustained); KDIP_CONV_PAIRMT=0: single CTAs
   if (p.mt == 2 && (m_tiles % 4 != 0 || (getenv("KDIP_CONV_PAIRMT") && atoi(getenv("KDIP_CONV_PAIRMT")) == 0))) p.pair = 0;
+  if (force_p1m2 && p.tma_epilogue) { p.mt = 2; p.pair = 1; }
   if (p.halo) {
     KDIP_REQUIRE(p.tma_epilogue, KDIP_EINVAL, "conv: internal error, halo pipeline without the TMA epilogue");
     // CTA pairs (M = 256 MMAs, weight rows split across the two CTAs) keep the per-SM shared-memory traffic of the N = 128 MMAs

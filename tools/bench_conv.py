@@ -11,6 +11,7 @@ iters = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 SHAPES = [  # H, Cin, Cout, taps, residual
     (256, 128, 128, 9, 1), (256, 256, 128, 9, 0), (128, 256, 256, 9, 1), (128, 128, 128, 9, 0), (64, 256, 256, 9, 1),
     (64, 512, 256, 9, 0), (32, 512, 512, 9, 0), (16, 512, 512, 9, 1), (256, 128, 128, 1, 0), (256, 128, 128, 9, 0),
+    (8, 512, 512, 9, 1), (16, 1024, 512, 9, 0), (32, 256, 256, 9, 1), (64, 128, 128, 9, 0), (32, 768, 256, 9, 0),
 ]
 only = os.environ.get("KDIP_BENCH_SHAPES")
 if only:
