@@ -32,5 +32,12 @@ graph = torch.cuda.CUDAGraph()
 with torch.cuda.graph(graph):
     step()
 graph.replay(); torch.cuda.synchronize()
-print("graph result matches:", torch.allclose(g, ref, rtol=1e-2, atol=1e-2 * ref.abs().max().item()), flush=True)
+def rel(a, b):
+    return ((a - b).norm() / b.norm()).item(), ((a - b).abs().max() / b.abs().max()).item()
+g_graph, out_graph = g.clone(), out.clone()
+step(); torch.cuda.synchronize()
+g_eager2, out_eager2 = g.clone(), out.clone()
+step(); torch.cuda.synchronize()
+print("eager vs eager   : vjp rel-L2 %.2e max %.2e | fwd rel-L2 %.2e max %.2e" % (rel(g, g_eager2) + rel(out, out_eager2)), flush=True)
+print("graph vs eager   : vjp rel-L2 %.2e max %.2e | fwd rel-L2 %.2e max %.2e" % (rel(g_graph, g_eager2) + rel(out_graph, out_eager2)), flush=True)
 print(f"graph replay:    {timeit(graph.replay):.2f} ms", flush=True)
