@@ -13,7 +13,8 @@ sigma is uniform across the batch inside a sampler call; the sigma-dependent bra
 per-pixel covariance) are decided on the host from the schedule value the sampler attaches to the sigma tensor, so a
 model evaluation has no device->host synchronisation except the CG convergence poll.
 
-Out of scope (not reachable from the BASELINE configurations): 'autoI' (needs gpytorch), 'stsl' / 'stsl+mle'.
+'stsl' / 'stsl+mle' (condition.py:185-208) is composed from the same pieces: 1 + num_hutchinson_samples UNet forward + VJP pairs.
+Out of scope: 'autoI' (a gpytorch Gaussian log-likelihood).
 """
 from abc import abstractmethod
 from warnings import warn  # noqa: F401  (mat solvers warn on CG non-convergence through kdip.ops)
@@ -94,7 +95,7 @@ class ConditionDenoiser(nn.Module):
         B = x.shape[0]
         sig = _uniform(_host_sigma(sigma, B))
         g = self.guidance
-        if g in ("dps+mle", "pgdm+mle"):
+        if g in ("dps+mle", "pgdm+mle", "stsl+mle"):
             g = "I" if sig < self.mle_sigma_thres else g.split("+")[0]
         x = x.detach().contiguous().float()
         if g == "uncond":
@@ -110,7 +111,9 @@ class ConditionDenoiser(nn.Module):
             return self._pgdm_guidance_impl(x, sigma)
         if g == "diffpir":
             return self._diffpir_guidance_impl(x, sigma)
-        if g in ("autoI", "stsl", "stsl+mle"):
+        if g == "stsl":
+            return self._stsl_guidance_impl(x, sigma)
+        if g == "autoI":
             raise NotImplementedError(f"guidance '{self.guidance}' is outside the kdip hot path (SURVEY.md §2 #2)")
         raise ValueError(f"Invalid guidance type: '{self.guidance}'.")
 
@@ -124,6 +127,38 @@ class ConditionDenoiser(nn.Module):
         g, direct = self._score(x0_mean, v)
         coef = float(np.float32(sig) ** 2 * np.float32(self.zeta)) / norm   # [B] device scalars: sigma^2 zeta / ||r_b||
         return ops.guidance_combine(x0_mean, g, direct, coef, self._ctx["c_in_dev"])
+
+    def _hutchinson_eps(self, x):
+        """One probe of the Hutchinson trace estimate (condition.py:198: torch.randn_like(x)); a hook so tests can inject the
+        reference's CPU draws."""
+        return torch.randn_like(x)
+
+    def _stsl_guidance_impl(self, x, sigma):
+        """condition.py:185-208.  loss = -zeta ||y - A x0(x)|| - (eta sigma^2 / (numel n)) sum_k <x0(x + eps_k) - x0(x), eps_k>, and
+        hat_x0 = x0 + sigma^2 grad_x loss.  With J(.) = d x0 / d x the gradient is
+            J(x)^T [ zeta A^T r / ||r||  +  w sum_k eps_k ]  -  w sum_k J(x + eps_k)^T eps_k,      w = eta sigma^2 / (numel n),
+        i.e. one input-VJP at x (seeded with the data term plus the summed probes) and one forward + VJP per probe; numel is
+        per image (the reference runs B = 1).  The probes are drawn first, in the reference's order."""
+        assert self.zeta is not None and self.eta is not None and self.num_hutchinson_samples is not None, \
+            "zeta, eta, and num_hutchinson_samples must be specified for STSL guidance"
+        B, n = x.shape[0], int(self.num_hutchinson_samples)
+        sig = np.float32(_uniform(_host_sigma(sigma, B)))
+        numel = x[0].numel()
+        w = float(np.float32(self.eta) / np.float32(numel) * sig ** 2 / np.float32(n)) if n > 0 else 0.0
+        one, w_dev, mw_dev = _dev([1.0] * B, x.device), _dev([w] * B, x.device), _dev([-w] * B, x.device)
+        x0_mean = self.uncond_pred(x, sigma)[0]
+        c_in_dev = self._ctx["c_in_dev"]
+        v, norm = self.operator.handle.dps_grad(self._y_for(B), x0_mean)       # A^T r, ||r|| per image
+        eps = [self._hutchinson_eps(x).to(x.device, torch.float32).contiguous() for _ in range(n)]
+        seed_vec = ops.lincomb(v, eps[0] if n else v, float(np.float32(self.zeta)) / norm, w_dev if n else _dev([0.0] * B, x.device))
+        for k in range(1, n):
+            seed_vec = ops.lincomb(seed_vec, eps[k], one, w_dev)
+        g, direct = self._score(x0_mean, seed_vec)
+        for k in range(n):
+            x0_k = self.uncond_pred(ops.lincomb(x, eps[k], one, one), sigma)[0]
+            g_k, direct_k = self._score(x0_k, eps[k])
+            g, direct = ops.lincomb(g, g_k, one, mw_dev), ops.lincomb(direct, direct_k, one, mw_dev)
+        return ops.guidance_combine(x0_mean, g, direct, _dev([float(sig ** 2)] * B, x.device), c_in_dev)
 
     def _pgdm_guidance_impl(self, x, sigma):
         """condition.py:150-157: theta = r^2 = sigma^2/(1+sigma^2); x0 + sigma^2 r^2 J^T mat."""

@@ -1,6 +1,6 @@
 """Oracle: mat solvers, x0-covariance rules and guidance combine (test infrastructure only).
 
-Follows condition/condition.py:83-183 (ConditionDenoiser.forward and the guidance impls), :231-274
+Follows condition/condition.py:83-208 (ConditionDenoiser.forward and the guidance impls), :231-274
 (ConditionOpenAIDenoiser.uncond_pred), :287-300 (V2 uncond_pred) and :317-439 (mat solvers).
 CG is scipy.sparse.linalg.cg with the legacy ``tol`` semantics of the reference's pinned environment
 (python 3.8 => scipy <= 1.10: stop when ||r|| <= tol*||b||), spelled rtol=tol, atol=0 on current scipy.
@@ -83,13 +83,14 @@ class ConditionDenoiserRef:
     """ConditionOpenAIDenoiser (condition.py:211-274) on top of the functional UNet oracle."""
 
     def __init__(self, sd, cfg, operator, measurement, guidance, x0_cov_type="pgdm", recon_mse=None,
-                 zeta=None, lambda_=None, mle_sigma_thres=0.2, ortho_tf_type=None):
+                 zeta=None, lambda_=None, mle_sigma_thres=0.2, ortho_tf_type=None, eta=None, num_hutchinson_samples=None):
         self.sd, self.cfg = sd, cfg
         self.sched = Schedule()
         self.operator = operator
         self.y = measurement[0] if isinstance(measurement, tuple) else measurement
         self.guidance, self.x0_cov_type = guidance, x0_cov_type
         self.recon_mse, self.zeta, self.lambda_ = recon_mse, zeta, lambda_
+        self.eta, self.num_hutchinson_samples = eta, num_hutchinson_samples
         self.thres = mle_sigma_thres
         self.ortho_tf_type = ortho_tf_type
         self.ot = OrthoTransform(ortho_tf_type)
@@ -135,7 +136,7 @@ class ConditionDenoiserRef:
         """condition.py:83-131."""
         assert x.shape[0] == 1
         g = self.guidance
-        if g in ("dps+mle", "pgdm+mle"):
+        if g in ("dps+mle", "pgdm+mle", "stsl+mle"):
             g = "I" if sigma < self.thres else g.split("+")[0]
         if g == "uncond":
             with torch.no_grad():
@@ -160,6 +161,19 @@ class ConditionDenoiserRef:
             norm = torch.linalg.norm(diff)
             score = -torch.autograd.grad(norm, x)[0] * self.zeta
             hat = x0_mean + sigma.pow(2) * score
+        elif g == "stsl":
+            # condition.py:185-208: first-order data term + Hutchinson estimate of the trace of the x0 Jacobian;
+            # eps is drawn from torch's global generator, one draw per sample, after the first uncond_pred
+            x = x.detach().requires_grad_()
+            x0_mean = self.uncond_pred(x, sigma)[0]
+            first = -torch.linalg.norm(self.y - self.operator.forward(x0_mean, noiseless=True))
+            second = 0
+            for _ in range(self.num_hutchinson_samples):
+                eps = torch.randn_like(x)
+                second = second + -((self.uncond_pred(x + eps, sigma)[0] - x0_mean) * eps).sum() * sigma.pow(2)
+            second = second / self.num_hutchinson_samples
+            loss = self.zeta * first + (self.eta / x.numel()) * second
+            hat = x0_mean + sigma.pow(2) * torch.autograd.grad(loss, x)[0]
         elif g == "diffpir":
             with torch.no_grad():
                 x0_mean = self.uncond_pred(x, sigma)[0]

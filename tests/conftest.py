@@ -28,3 +28,8 @@ def golden_ffhq():
 @pytest.fixture(scope="session")
 def golden_v2():
     return np.load(os.path.join(ROOT, "tests", "golden", "golden_v2.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_stsl():
+    return np.load(os.path.join(ROOT, "tests", "golden", "golden_stsl.npz"))

@@ -80,3 +80,11 @@ def v2_out_cov(seed=9):
     """Random-init out_cov head (k_diffusion/external.py:141): weight [6,128,1,1], bias [6]."""
     g = _g(seed)
     return torch.randn(6, 128, 1, 1, generator=g) * 0.05, torch.randn(6, generator=g) * 0.5 - 1.0
+
+
+# ---- STSL guidance (condition.py:185-208): (operator, sigma, zeta, eta, num_hutchinson_samples, torch seed of the eps draws) ----
+STSL_CASES = [
+    ("gaussian_blur", 1.0, 1.0, 2000.0, 2, 77),
+    ("inpainting", 0.3, 0.5, 1.0e5, 1, 78),
+    ("super_resolution", 3.0, 1.0, 300.0, 2, 79),
+]

@@ -252,3 +252,46 @@ def test_v2_denoiser_type_II_guidance(ot, sigma, golden_v2):
                                     mle_sigma_thres=1.0, ortho_tf_type=ot).eval()
     hat2 = cm2(xt.expand(2, -1, -1, -1).contiguous(), torch.full((2,), sigma).cuda())
     assert errs(hat2[1:2], hat)[1] < 1e-2
+
+
+@pytest.mark.parametrize("case", I.STSL_CASES, ids=lambda c: f"{c[0]}-{c[1]}")
+def test_stsl_guidance(case, tiny_model, golden_stsl):
+    """STSL (condition.py:185-208): DPS data term + Hutchinson second-order term, composed on the GPU from 1 + n UNet forward + VJP
+    pairs, vs the reference's own output (tests/golden/make_golden_stsl.py) on the same probes eps (the reference's CPU draws are
+    injected through the _hutchinson_eps hook).  Tolerance as in the module docstring: the per-evaluation floor, or twice the
+    reference's own sensitivity to bf16 weight rounding where that is larger (sigma = 3 with eta sigma^4 weighting)."""
+    from condition.condition import ConditionOpenAIDenoiser
+    from oracle import guidance_ref
+    model, diffusion = tiny_model
+    opname, sigma, zeta, eta, n, seed = case
+    op = make_op(opname, 64)
+    kw = dict(zeta=zeta, eta=eta, num_hutchinson_samples=n)
+
+    def run(batch):
+        cm = ConditionOpenAIDenoiser(inner_model=model, diffusion=diffusion, x0_cov_type="pgdm", recon_mse=None, operator=op,
+                                     measurement=measurement(op, opname, batch=batch), guidance="stsl", device="cuda", **kw).eval()
+        torch.manual_seed(seed)
+        cm._hutchinson_eps = lambda x: torch.randn(1, *x.shape[1:]).expand(x.shape[0], -1, -1, -1)
+        return cm(I.xt(64, sigma, seed=21).cuda().expand(batch, -1, -1, -1).contiguous(), torch.full((batch,), sigma).cuda())
+
+    hat = run(1)
+    assert torch.isfinite(hat).all()
+    gold = torch.as_tensor(golden_stsl[f"stsl.{opname}.{sigma}"])
+    e_max, e_l2 = errs(hat, gold)
+    frac = ((hat.cpu() - gold).abs() > 6e-2).float().mean().item()
+    cfg, sd_b = bf16_weight_oracle()
+    ref_op, meas = oracle_measurement(opname)
+    probe = guidance_ref.ConditionDenoiserRef(sd_b, cfg, ref_op, meas, "stsl", "pgdm", **kw)
+    torch.manual_seed(seed)
+    p = probe(I.xt(64, sigma, seed=21), torch.tensor([sigma]))
+    s_l2 = errs(p, gold)[1]
+    s_frac = ((p - gold).abs() > 6e-2).float().mean().item()
+    print(f"stsl {opname} sigma={sigma}: max {e_max:.3e} l2 {e_l2:.3e} frac>6e-2 {frac:.4f} | reference bf16-weight sensitivity l2 "
+          f"{s_l2:.3e} frac {s_frac:.4f}")
+    assert e_l2 <= max(3e-2, 2 * s_l2) and frac <= max(0.03, 3 * s_frac)
+    # the Hutchinson term is really there: the eta = 0 reference output is much further away than the tolerance
+    assert errs(golden_stsl[f"stsl.{opname}.{sigma}.eta0"], gold)[1] > 3 * max(e_l2, 1e-2)
+    # batch of 2 identical problems == the single problem
+    b_l2 = errs(run(2)[1:2], hat)[1]
+    print(f"   batch-of-2 vs single: l2 {b_l2:.3e}")
+    assert b_l2 <= max(1e-2, 2 * s_l2)

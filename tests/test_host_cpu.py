@@ -161,3 +161,56 @@ def test_two_rank_gloo_shard_and_gather(tmp_path):
     for p in procs:
         out, _ = p.communicate(timeout=180)
         assert p.returncode == 0, out.decode()
+
+
+@pytest.mark.parametrize("case", I.STSL_CASES[:2], ids=lambda c: f"{c[0]}-{c[1]}")
+def test_stsl_host_composition_against_reference_golden(case, golden_stsl, monkeypatch):
+    """ConditionDenoiser._stsl_guidance_impl composes STSL (condition.py:185-208) from explicit input-VJPs instead of autograd on
+    the loss.  Here the host code itself runs on CPU with its device pieces (UNet forward / VJP, dps_grad, lincomb, combine)
+    replaced by oracle-backed stand-ins, and must reproduce the REFERENCE's output: this pins the decomposition, the
+    coefficients and the order of the probe draws without a GPU (the GPU parity test then checks the kernels)."""
+    from oracle import guidance_ref, operators_ref, unet_ref
+    from condition import condition as C
+    opname, sigma, zeta, eta, n, seed = case
+    cfg = unet_ref.tiny_config()
+    sd = unet_ref.init_state_dict(cfg, seed=0)
+    ref_op = {"gaussian_blur": lambda: operators_ref.BlurOperator("gaussian_blur", 0.05, in_shape=(1, 3, 64, 64)),
+              "inpainting": lambda: operators_ref.InpaintingOperator(0.05, operators_ref.box_mask(64, 32))}[opname]()
+    x0 = I.image(64, batch=1, seed=1)
+    torch.manual_seed(2)
+    meas = ref_op.forward(x0.clone(), flatten=True)
+    oracle = guidance_ref.ConditionDenoiserRef(sd, cfg, ref_op, meas, "stsl", "pgdm")
+
+    class Handle:
+        def dps_grad(self, y, x0m):
+            x0g = x0m.detach().requires_grad_()
+            nrm = torch.linalg.norm(y - ref_op.forward(x0g, noiseless=True))
+            return -torch.autograd.grad(nrm, x0g)[0] * nrm.detach(), nrm.detach().reshape(1)
+
+    class Op:
+        name, handle = opname, Handle()
+
+    class Host(C.ConditionDenoiser):
+        def uncond_pred(self, x, sigma):
+            xg = x.detach().requires_grad_()
+            x0m = oracle.uncond_pred(xg, sigma)[0]
+            self._ctx = dict(c_in_dev=torch.ones(1), xg=xg, x0m=x0m)
+            return x0m.detach(), None, None
+
+        def _score(self, x0_mean, v):
+            assert torch.equal(x0_mean, self._ctx["x0m"].detach()), "VJP requested for a stale forward"
+            return torch.autograd.grad((self._ctx["x0m"] * v).sum(), self._ctx["xg"])[0], torch.zeros_like(v)
+
+    bc = lambda a: torch.as_tensor(a, dtype=torch.float32).reshape(-1, 1, 1, 1)
+    monkeypatch.setattr(C.ops, "lincomb", lambda x, y, a, c: bc(a) * x + bc(c) * y)
+    monkeypatch.setattr(C.ops, "guidance_combine",
+                        lambda x0m, g, d, coef, c_in=None: (x0m + bc(coef) * (bc(c_in) * g + d)).clip(-1, 1))
+    torch.set_grad_enabled(True)
+    for e, key in ((eta, f"stsl.{opname}.{sigma}"), (0.0, f"stsl.{opname}.{sigma}.eta0")):
+        cm = Host(operator=Op(), measurement=meas, guidance="stsl", zeta=zeta, eta=e, num_hutchinson_samples=n)
+        torch.manual_seed(seed)
+        hat = cm(I.xt(64, sigma, seed=21), torch.tensor([sigma]))
+        ref = torch.from_numpy(golden_stsl[key])
+        err = (hat - ref).abs().max().item()
+        assert err < 2e-3, (key, err)
+    assert (torch.from_numpy(golden_stsl[f"stsl.{opname}.{sigma}"]) - ref).norm() / ref.norm() > 0.05   # the probes matter
