@@ -263,6 +263,11 @@ int kdip_unet_forward(kdip_unet* u, const float* x, const float* x_scale, const 
  * condition/condition.py:136,146,155,172,269).  seed [N,6,S,S] fp32. */
 int kdip_unet_vjp(kdip_unet* u, const float* seed, int N, float* grad_x, void* workspace, size_t ws_bytes,
                   kdip_stream_t s);
+/* Make (N, workspace) the handle's current launch plan WITHOUT launching anything (host-side only).  A caller that replays
+ * a captured CUDA graph of kdip_unet_forward (the library is "safe under CUDA-graph capture", SURVEY.md 8(b) threading row)
+ * bypasses the library, so the handle would still remember the batch of its last direct call; call this before such a replay
+ * so that a following kdip_unet_vjp / kdip_unet_feature sees the batch whose activations really are in `workspace`. */
+int kdip_unet_prepare(kdip_unet* u, int N, void* workspace, size_t ws_bytes);
 
 /* Instrumented forward + input-VJP: the same launch lists with a CUDA-event pair around every step, summed by class.
  * Used by bench.py for the live roofline of the dominant kernel (conv_gemm_kernel); synchronises the stream. */

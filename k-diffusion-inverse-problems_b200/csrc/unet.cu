@@ -946,6 +946,11 @@ static int ensure_plan(kdip_unet* u, int N, void* ws, size_t ws_bytes) {
   return build_launch_plan(u, N, ws, ws_bytes, &need);
 }
 
+extern "C" int kdip_unet_prepare(kdip_unet* u, int N, void* workspace, size_t ws_bytes) {
+  KDIP_REQUIRE(u && N > 0, KDIP_EINVAL, "unet_prepare: bad argument");
+  return ensure_plan(u, N, workspace, ws_bytes);
+}
+
 // drop a cached per-pointer plan that is about to be replaced
 static void retire_plan(kdip_unet* u, ConvPlan* old) {
   if (!old) return;

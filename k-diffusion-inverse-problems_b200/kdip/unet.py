@@ -82,8 +82,12 @@ class UNetEngine:
 
     def _replay(self, key, statics_fn, launch_fn):
         """Returns the (graph, static buffers) for `key` once two eager calls have happened, else None."""
+        if not self._graphs_on:
+            return None
+        if key not in self._replays and len(self._replays) >= 16:     # bound the static buffers kept for shapes no longer in use
+            self._replays.pop(next(iter(self._replays)))
         r = self._replays.setdefault(key, {"calls": 0, "graph": None, "bufs": None, "failed": False})
-        if not self._graphs_on or r["failed"]:
+        if r["failed"]:
             return None
         r["calls"] += 1
         if r["calls"] <= 2:
@@ -138,6 +142,7 @@ class UNetEngine:
             b["x"].copy_(x); b["t"].copy_(t)
             if x_scale is not None:
                 b["xs"].copy_(x_scale)
+            check(lib.kdip_unet_prepare(self._h, N, ws, ws_bytes))   # the replay bypasses the library: keep its (N, workspace) current
             r["graph"].replay()
             out.copy_(b["out"])
             if want_cov:
@@ -192,6 +197,7 @@ class UNetEngine:
         r = self._replay(("vjp", N, H, W, self._ws.data_ptr()), statics, launch)
         if r is not None:
             r["bufs"]["seed"].copy_(seed)
+            check(lib.kdip_unet_prepare(self._h, N, ws, ws_bytes))
             r["graph"].replay()
             out.copy_(r["bufs"]["grad"])
         else:

@@ -132,3 +132,22 @@ def test_cuda_graph_replay_matches_eager_launches(tiny_engine):
     x2 = I.unet_input(64, batch=3, seed=53).cuda()
     o2 = eng.forward(x2, t)
     assert _errs(o2, outs[0])[1] > 0.1
+
+
+def test_cuda_graph_replay_interleaved_batches(tiny_engine):
+    """A replayed forward bypasses the library, which remembers the batch of its last direct call; the engine re-arms the handle
+    (kdip_unet_prepare) before every replay so that a VJP / feature read after a replayed forward of ANOTHER batch size works."""
+    cfg, sd, eng = tiny_engine
+    xa, ta = I.unet_input(64, batch=2, seed=61).cuda(), torch.tensor([10, 600]).cuda()
+    xb, tb = I.unet_input(64, batch=4, seed=62).cuda(), torch.tensor([1, 200, 640, 998]).cuda()
+    va, vb = I.unet_seed((2, 6, 64, 64), seed=63).cuda(), I.unet_seed((4, 6, 64, 64), seed=64).cuda()
+    first = {}
+    for it in range(5):
+        for tag, x, t, v in (("a", xa, ta, va), ("b", xb, tb, vb)):
+            out = eng.forward(x, t).clone()
+            g = eng.vjp(v).clone()
+            if it == 0:
+                first[tag] = (out, g)
+            else:
+                assert _errs(out, first[tag][0])[1] < 1.5e-2 and _errs(g, first[tag][1])[1] < 3e-2, (it, tag)
+    assert not any(r["failed"] for r in eng._replays.values())
