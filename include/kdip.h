@@ -115,6 +115,27 @@ int kdip_gather(const float* src, const int32_t* idx, float* dst, int B, int CHW
 int kdip_scatter(const float* src, const int32_t* idx, float* dst, int B, int CHW, int M, kdip_stream_t s);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Data front end and evaluation reductions: the callers either side of the sampling path.
+ * 8-bit images are interleaved HWC (PIL / PNG order), fp32 images NCHW in [-1, 1]; H*W must be a multiple of 4.
+ */
+/* Dataset transform of sample_condition_openai.py:140-144 (torchvision ToTensor, then x*2-1): dst = u8/255*2-1. Bit-exact. */
+int kdip_images_u8_to_f32(const uint8_t* src_hwc, float* dst_nchw, int B, int H, int W, kdip_stream_t s);
+/* k_diffusion/utils.py:24-31 to_pil_image: dst = trunc((clamp(x,-1,1)+1)/2*255) (torchvision mul(255).byte()). Bit-exact. */
+int kdip_images_f32_to_u8(const float* src_nchw, uint8_t* dst_hwc, int B, int H, int W, kdip_stream_t s);
+/* out[b] (fp64, device) = sum over the image of (a-b)^2.  to_eval_first != 0 maps both through (x/2+0.5).clip(0,1) and
+ * subtracts in fp64 (PSNR of sample_condition_openai.py:41-44 = 10 log10(CHW / out[b])); 0 = fp32 differences
+ * (analytic_variance.py:129).  Zeroes `out` itself. */
+int kdip_sqerr_sum(const float* a, const float* b, int to_eval_first, double* out, int B, int CHW, kdip_stream_t s);
+/* analytic_variance.py:128-129 fused: hat_x0 = x_noised + eps*(-sigma[b]) with eps = channels 0..2 of unet_out [B,6,H,W]
+ * (OpenAIDenoiser.forward, k_diffusion/external.py:111-132); out[b] = sum (x0 - hat_x0)^2 (fp64); hat_x0 written if non-NULL. */
+int kdip_denoise_sqerr(const float* unet_out, const float* x_noised, const float* x0, const float* sigma, double* out,
+                       float* hat_x0, int B, int HW, kdip_stream_t s);
+/* out[b] = sum over 3 channels and all window-valid centres of the SSIM map of to_eval(a), to_eval(b)
+ * (skimage.metrics.structural_similarity(channel_axis=0, data_range=1), sample_condition_openai.py:45: 7x7 uniform window,
+ * sample covariance, K1 0.01, K2 0.03); SSIM = out[b] / (3 (H-6) (W-6)). */
+int kdip_ssim_sum(const float* a, const float* b, double* out, int B, int H, int W, kdip_stream_t s);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Measurement operators and mat solvers — condition/measurements.py:86-244 (operators), condition/condition.py:317-439
  * (inpainting_mat / gaussian_blur_mat / motion_blur_mat / super_resolution_mat), condition/utils.py:50-139
  * (OrthoTransform), condition/diffpir_utils/utils_sisr.py:9-96, condition/dps_utils/resizer.py:8-198.

@@ -50,7 +50,8 @@ class DiscreteSchedule(nn.Module):
     def sigma_to_t_host(self, sigma):
         """Same piecewise-linear inverse evaluated on the host in fp32 (no device work, no sync): sigma float -> t float."""
         ls = self._log_sigmas_host
-        log_sigma = np.log(np.float32(sigma))
+        with np.errstate(divide='ignore'):          # sigma = 0 (analytic_variance.py evaluates the trailing 0): log -> -inf, t -> 0
+            log_sigma = np.log(np.float32(sigma))
         low_idx = min(int(np.count_nonzero(log_sigma - ls >= 0)) - 1, len(ls) - 2)
         if np.count_nonzero(log_sigma - ls >= 0) == 0:
             low_idx = 0   # cumsum().argmax() of an all-False column is 0

@@ -261,3 +261,58 @@ def scatter(src, idx, shape):
     dst = torch.empty(B, *shape, device=src.device, dtype=torch.float32)
     check(lib.kdip_scatter(ptr(_f32(src)), ptr(idx), ptr(dst), B, dst[0].numel(), idx.numel(), stream_ptr()))
     return dst
+
+
+# ---- data front end / evaluation reductions (csrc/images.cu) ------------------------------------------------------------------
+
+def images_u8_to_f32(u8_hwc):
+    """[B,H,W,3] uint8 CUDA (PIL order) -> [B,3,H,W] fp32 in [-1,1]: ToTensor then x*2-1 (sample_condition_openai.py:140-144)."""
+    assert u8_hwc.dtype == torch.uint8 and u8_hwc.dim() == 4 and u8_hwc.shape[-1] == 3
+    B, H, W, _ = u8_hwc.shape
+    out = torch.empty(B, 3, H, W, device=u8_hwc.device, dtype=torch.float32)
+    check(lib.kdip_images_u8_to_f32(ptr(u8_hwc), ptr(out), B, H, W, stream_ptr()))
+    return out
+
+
+def images_f32_to_u8(x):
+    """[B,3,H,W] fp32 -> [B,H,W,3] uint8 as k_diffusion.utils.to_pil_image would store it (utils.py:24-31)."""
+    x = _f32(x)
+    B, _, H, W = x.shape
+    out = torch.empty(B, H, W, 3, device=x.device, dtype=torch.uint8)
+    check(lib.kdip_images_f32_to_u8(ptr(x), ptr(out), B, H, W, stream_ptr()))
+    return out
+
+
+def sqerr_sum(a, b, to_eval_first=False):
+    """Per-image sum of squared differences, fp64 [B] (device)."""
+    a, b = _f32(a), _f32(b)
+    B = a.shape[0]
+    out = torch.empty(B, device=a.device, dtype=torch.float64)
+    check(lib.kdip_sqerr_sum(ptr(a), ptr(b), int(to_eval_first), ptr(out), B, a[0].numel(), stream_ptr()))
+    return out
+
+
+def denoise_sqerr(unet_out, x_noised, x0, sigma_dev, want_hat=False):
+    """analytic_variance.py:128-129: per-image sum (x0 - (x_noised - sigma*eps))^2 as fp64 [B] (and hat_x0 if asked)."""
+    unet_out, x_noised, x0 = _f32(unet_out), _f32(x_noised), _f32(x0)
+    B, _, H, W = x0.shape
+    out = torch.empty(B, device=x0.device, dtype=torch.float64)
+    hat = torch.empty_like(x0) if want_hat else None
+    check(lib.kdip_denoise_sqerr(ptr(unet_out), ptr(x_noised), ptr(x0), ptr(_f32(sigma_dev)), ptr(out), ptr(hat), B, H * W, stream_ptr()))
+    return (out, hat) if want_hat else out
+
+
+def psnr(x0, hat_x0):
+    """peak_signal_noise_ratio(to_eval(x0), to_eval(hat_x0), data_range=1) per image, fp64 [B] (sample_condition_openai.py:41-44)."""
+    n = x0[0].numel()
+    return 10.0 * torch.log10(n / sqerr_sum(x0, hat_x0, to_eval_first=True))
+
+
+def ssim(x0, hat_x0):
+    """structural_similarity(to_eval(x0), to_eval(hat_x0), channel_axis=0, data_range=1) per image, fp64 [B] (:45)."""
+    a, b = _f32(x0), _f32(hat_x0)
+    B, C, H, W = a.shape
+    assert C == 3
+    out = torch.empty(B, device=a.device, dtype=torch.float64)
+    check(lib.kdip_ssim_sum(ptr(a), ptr(b), ptr(out), B, H, W, stream_ptr()))
+    return out / (3.0 * (H - 6) * (W - 6))
