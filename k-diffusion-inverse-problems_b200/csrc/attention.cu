@@ -245,6 +245,7 @@ int launch_attention_fwd(const bf16* qkv, int N, int T, int heads, int ch, bf16*
   KDIP_REQUIRE(ch == CH, KDIP_ESHAPE, "attention: head channels must be 64 (got %d)", ch);
   KDIP_REQUIRE(T % KC == 0, KDIP_ESHAPE, "attention: T=%d must be a multiple of 64", T);
   if (attention_tc_supported(T, ch)) return launch_attention_fwd_tc(qkv, N, T, heads, out, lse, s);
+  if (attention_tcs_supported(T, ch)) return launch_attention_fwd_tcs(qkv, N, T, heads, out, lse, s);
   const size_t smem = (size_t)(2 * QB + 2 * KC) * LD * sizeof(float);
   static bool once = false;
   if (!once) { int rc = set_smem((const void*)attn_fwd_kernel, smem); if (rc) return rc; once = true; }
@@ -259,6 +260,8 @@ int launch_attention_bwd(const bf16* qkv, const bf16* out, const bf16* d_out, co
   KDIP_REQUIRE(T % KC == 0, KDIP_ESHAPE, "attention: T=%d must be a multiple of 64", T);
   if (attention_tc_supported(T, ch) && !(getenv("KDIP_ATTN_TC_BWD") && atoi(getenv("KDIP_ATTN_TC_BWD")) == 0))
     return launch_attention_bwd_tc(qkv, out, d_out, lse, N, T, heads, dqkv, s);
+  if (attention_tcs_supported(T, ch) && !(getenv("KDIP_ATTN_TC_BWD") && atoi(getenv("KDIP_ATTN_TC_BWD")) == 0))
+    return launch_attention_bwd_tcs(qkv, out, d_out, lse, N, T, heads, dqkv, s);
   const size_t smem_q = (size_t)(3 * QB + 2 * KC) * LD * sizeof(float);
   const size_t smem_kv = (size_t)((4 * QB + 2 * KC) * LD + 2 * KC) * sizeof(float);
   static bool once = false;

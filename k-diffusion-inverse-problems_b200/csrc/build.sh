@@ -13,7 +13,7 @@ for src in "$HERE"/*.cu; do
   obj="$HERE/build/$(basename "${src%.cu}").o"
   OBJS="$OBJS $obj"
   if [ ! -f "$obj" ] || [ "$src" -nt "$obj" ] || [ "$HERE/kdip_common.cuh" -nt "$obj" ] || [ "$HERE/../../include/kdip.h" -nt "$obj" ] \
-     || [ "$HERE/unet_kernels.cuh" -nt "$obj" ] || [ "$HERE/fft.cuh" -nt "$obj" ] || [ "$0" -nt "$obj" ]; then
+     || [ "$HERE/unet_kernels.cuh" -nt "$obj" ] || [ "$HERE/fft.cuh" -nt "$obj" ] || [ "$HERE/attention_tc.cuh" -nt "$obj" ] || [ "$0" -nt "$obj" ]; then
     # a source may ask for extra flags with a line "// NVCC_FLAGS: ..." (e.g. -fmad=false where the reference's
     # separately-rounded mul/add order must be reproduced)
     extra=$(grep -m1 -oP '(?<=^// NVCC_FLAGS: ).*' "$src" || true)

@@ -77,6 +77,11 @@ int launch_attention_bwd(const bf16* qkv, const bf16* out, const bf16* d_out, co
 // tcgen05 / TMEM / TMA versions for T in {64, 128, 256} (attention_tc.cu); the launchers above dispatch to them when supported
 bool attention_tc_supported(int T, int ch);
 int launch_attention_fwd_tc(const bf16* qkv, int N, int T, int heads, bf16* out, float* lse, cudaStream_t s);
+// streamed-block versions for T >= 384, T % 128 == 0 (attention_tcs.cu: the T = 1024 level of the ImageNet UNet)
+bool attention_tcs_supported(int T, int ch);
+int launch_attention_fwd_tcs(const bf16* qkv, int N, int T, int heads, bf16* out, float* lse, cudaStream_t s);
+int launch_attention_bwd_tcs(const bf16* qkv, const bf16* out, const bf16* d_out, const float* lse, int N, int T, int heads,
+                             bf16* dqkv, cudaStream_t s);
 int launch_attention_bwd_tc(const bf16* qkv, const bf16* out, const bf16* d_out, const float* lse, int N, int T, int heads, bf16* dqkv,
                             cudaStream_t s);
 
