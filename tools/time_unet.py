@@ -17,7 +17,7 @@ t = torch.full((B,), 500.0, device="cuda")
 seed = torch.randn(B, 6, 256, 256, device="cuda")
 out = torch.empty(B, 6, 256, 256, device="cuda")
 g = torch.empty(B, 3, 256, 256, device="cuda")
-for _ in range(2):
+for _ in range(4):     # the engine captures its CUDA graphs on the third call of a shape
     eng.forward(x, t, out=out); eng.vjp(seed, out=g)
 torch.cuda.synchronize()
 e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
