@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 rm -f gpurun_out/summary.txt
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
-for f in ${@:-tests/test_elementwise_gpu.py tests/test_conv_gemm_gpu.py tests/test_layers_gpu.py tests/test_unet_gpu.py tests/test_operators_gpu.py tests/test_guidance_gpu.py}; do
+for f in ${@:-tests/test_elementwise_gpu.py tests/test_conv_gemm_gpu.py tests/test_layers_gpu.py tests/test_unet_gpu.py tests/test_operators_gpu.py tests/test_guidance_gpu.py tests/test_frontend_gpu.py}; do
   name=$(basename "$f" .py)
   timeout 900 python -m pytest "$f" -m gpu -q -s -p no:cacheprovider > "gpurun_out/$name.log" 2>&1
   echo "== $name exit $? ==" | tee -a gpurun_out/summary.txt
