@@ -47,6 +47,11 @@ int kdip_churn(float* x, const float* noise, float s_noise, float sigma, float s
 int kdip_euler_step(const float* x, const float* denoised, float sigma_hat, float dt, float* x_out, float* d_out,
                     size_t n, kdip_stream_t s);
 /* d2 = (x2 - denoised2)/sigma_next ; x_out = x + (d + d2)/2 * dt                       (sampling.py:180-183) */
+/* out = a*x + b*y + c*z, host scalars, products and sums rounded separately; y / z may be NULL; out may alias an input.
+ * The state update of the remaining k_diffusion/sampling.py samplers (sample_euler_ancestral :139-156, sample_dpm_2 :187-215,
+ * sample_dpm_2_ancestral :218-248, sample_lms :259-275, sample_dpmpp_2s_ancestral :507-538, sample_dpmpp_2m :583-606).       */
+int kdip_lincomb3(const float* x, const float* y, const float* z, float a, float b, float c, float* out, size_t n,
+                  kdip_stream_t s);
 int kdip_heun_step(const float* x, const float* d, const float* x2, const float* denoised2, float sigma_next, float dt,
                    float* x_out, size_t n, kdip_stream_t s);
 

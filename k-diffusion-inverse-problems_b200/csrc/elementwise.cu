@@ -57,6 +57,26 @@ __global__ void heun_kernel(const float* __restrict__ x, const float* __restrict
   }
 }
 
+// out = a*x + b*y + c*z with host scalars, evaluated as ((a*x) + (b*y)) + (c*z), each product and sum rounded separately
+// (this file is built with -fmad=false); y / z may be NULL.  The update of every other k-diffusion sampler is one or two of these.
+template <int TERMS>
+__global__ void lincomb3_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ z, float a,
+                                float b, float c, float* __restrict__ out, size_t n4) {
+  EW_LOOP(i, n4) {
+    float4 o = ld4(x, i);
+    o.x = a * o.x; o.y = a * o.y; o.z = a * o.z; o.w = a * o.w;
+    if (TERMS >= 2) {
+      const float4 v = ld4(y, i);
+      o.x = o.x + b * v.x; o.y = o.y + b * v.y; o.z = o.z + b * v.z; o.w = o.w + b * v.w;
+    }
+    if (TERMS >= 3) {
+      const float4 v = ld4(z, i);
+      o.x = o.x + c * v.x; o.y = o.y + c * v.y; o.z = o.z + c * v.z; o.w = o.w + c * v.w;
+    }
+    st4(out, i, o);
+  }
+}
+
 // ---- p_mean_variance epilogue ----------------------------------------------------------------------------------------
 // grid.y = image; each thread handles 4 pixels of all 3 channels.
 __global__ void pmv_kernel(const float* __restrict__ out, const float* __restrict__ x, const kdip_pmv_scalars* __restrict__ sc,
@@ -241,6 +261,19 @@ extern "C" int kdip_heun_step(const float* x, const float* d, const float* x2, c
   REQ_ALIGN16(x); REQ_ALIGN16(d); REQ_ALIGN16(x2); REQ_ALIGN16(denoised2); REQ_ALIGN16(x_out); REQ_MULT4(n);
   KDIP_REQUIRE(sigma_next > 0.f, KDIP_EINVAL, "heun_step: sigma_next must be > 0");
   heun_kernel<<<ew_grid(n / 4, EW_THREADS), EW_THREADS, 0, (cudaStream_t)s>>>(x, d, x2, denoised2, sigma_next, dt, x_out, n / 4);
+  KDIP_LAUNCH_CHECK();
+  return KDIP_OK;
+}
+
+extern "C" int kdip_lincomb3(const float* x, const float* y, const float* z, float a, float b, float c, float* out, size_t n,
+                             kdip_stream_t s) {
+  REQ_ALIGN16(x); REQ_ALIGN16(y); REQ_ALIGN16(z); REQ_ALIGN16(out); REQ_MULT4(n);
+  KDIP_REQUIRE(x != nullptr && out != nullptr, KDIP_EINVAL, "lincomb3: x and out are required");
+  KDIP_REQUIRE(y != nullptr || z == nullptr, KDIP_EINVAL, "lincomb3: z without y");
+  const dim3 g = ew_grid(n / 4, EW_THREADS);
+  if (z) lincomb3_kernel<3><<<g, EW_THREADS, 0, (cudaStream_t)s>>>(x, y, z, a, b, c, out, n / 4);
+  else if (y) lincomb3_kernel<2><<<g, EW_THREADS, 0, (cudaStream_t)s>>>(x, y, z, a, b, c, out, n / 4);
+  else lincomb3_kernel<1><<<g, EW_THREADS, 0, (cudaStream_t)s>>>(x, y, z, a, b, c, out, n / 4);
   KDIP_LAUNCH_CHECK();
   return KDIP_OK;
 }

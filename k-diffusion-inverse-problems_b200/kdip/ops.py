@@ -249,6 +249,15 @@ def heun_step(x, d, x2, denoised2, sigma_next, dt):
     return x_out
 
 
+def lincomb3(x, a, y=None, b=0.0, z=None, c=0.0, out=None):
+    """a*x + b*y + c*z with host scalars (kdip_lincomb3); y / z optional."""
+    x = _f32(x)
+    out = torch.empty_like(x) if out is None else out
+    check(lib.kdip_lincomb3(ptr(x), ptr(_f32(y)) if y is not None else None, ptr(_f32(z)) if z is not None else None,
+                            float(a), float(b), float(c), ptr(out), x.numel(), stream_ptr()))
+    return out
+
+
 def gather(src, idx):
     B, M = src.shape[0], idx.numel()
     dst = torch.empty(B, M, device=src.device, dtype=torch.float32)

@@ -33,3 +33,8 @@ def golden_v2():
 @pytest.fixture(scope="session")
 def golden_stsl():
     return np.load(os.path.join(ROOT, "tests", "golden", "golden_stsl.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_samplers():
+    return np.load(os.path.join(ROOT, "tests", "golden", "golden_samplers.npz"))

@@ -88,3 +88,38 @@ STSL_CASES = [
     ("inpainting", 0.3, 0.5, 1.0e5, 1, 78),
     ("super_resolution", 3.0, 1.0, 300.0, 2, 79),
 ]
+
+
+# ---- the other k_diffusion samplers (make_golden_samplers.py) ----------------------------------------
+SAMPLER_N, SAMPLER_SIGMA_MIN, SAMPLER_SIGMA_MAX = 10, 0.05, 20.0
+SAMPLER_SHAPE = (2, 3, 16, 16)
+SAMPLER_NOISE_SEED = 17
+
+
+def SAMPLER_MODEL(x, sigma, **kw):
+    """Analytic denoiser: posterior mean of N(0.1-shifted, I) data under the Karras forward process, up to the shift."""
+    return x / (1 + sigma.view(-1, 1, 1, 1) ** 2) + 0.1
+
+
+def sampler_start():
+    return torch.randn(*SAMPLER_SHAPE, generator=_g(23)) * SAMPLER_SIGMA_MAX
+
+
+def sampler_noises():
+    """What torch.randn_like(x) returns step by step after torch.manual_seed(SAMPLER_NOISE_SEED) (CPU generator)."""
+    g = torch.Generator().manual_seed(SAMPLER_NOISE_SEED)
+    return [torch.randn(*SAMPLER_SHAPE, generator=g) for _ in range(SAMPLER_N)]
+
+
+EXTRA_SAMPLER_CASES = [
+    ("euler_ancestral", dict(eta=1.0, s_noise=1.0)),
+    ("euler_ancestral/eta0.5", dict(eta=0.5, s_noise=1.003)),
+    ("dpm_2", dict()),
+    ("dpm_2/churn", dict(s_churn=40., s_tmin=0.05, s_tmax=50., s_noise=1.003)),
+    ("dpm_2_ancestral", dict(eta=1.0, s_noise=1.0)),
+    ("lms", dict(order=4)),
+    ("lms/order2", dict(order=2)),
+    ("dpmpp_2s_ancestral", dict(eta=1.0, s_noise=1.0)),
+    ("dpmpp_2s_ancestral/eta0", dict(eta=0.0)),
+    ("dpmpp_2m", dict()),
+]

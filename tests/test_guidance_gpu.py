@@ -295,3 +295,55 @@ def test_stsl_guidance(case, tiny_model, golden_stsl):
     b_l2 = errs(run(2)[1:2], hat)[1]
     print(f"   batch-of-2 vs single: l2 {b_l2:.3e}")
     assert b_l2 <= max(1e-2, 2 * s_l2)
+
+
+@pytest.mark.parametrize("case", I.EXTRA_SAMPLER_CASES, ids=lambda c: c[0])
+def test_extra_samplers(case, golden_samplers):
+    """The remaining k_diffusion samplers (sampling.py:139-275,507-606): host-fp32 step coefficients +
+    kdip_euler_step / kdip_lincomb3 updates vs the oracle loops AND vs the reference's own output (golden_samplers) on identical
+    noise with the analytic denoiser.  Tolerance 2e-5 of the output scale over 10 steps (folded coefficients differ from the
+    reference's operation order by an ulp per step)."""
+    import k_diffusion as K
+    from oracle import sampler_ref
+    name, kw = case
+    base = name.split("/")[0]
+    noises, xT = I.sampler_noises(), I.sampler_start()
+    sig = sampler_ref.get_sigmas_karras(I.SAMPLER_N, I.SAMPLER_SIGMA_MIN, I.SAMPLER_SIGMA_MAX)
+    okw, pkw = dict(kw), dict(kw)
+    if "ancestral" in name:
+        okw["noise_fn"] = lambda i, x: noises[i]
+        by_sigma = {float(s): k for k, s in enumerate(sig[:-1])}
+        pkw["noise_sampler"] = lambda s, s_next: noises[by_sigma[float(s)]]
+    elif base == "dpm_2":
+        okw["noise_fn"] = lambda i, x: noises[i]
+        pkw["noise_sampler"] = lambda i, x: noises[i].to(x.device)
+    ref = getattr(sampler_ref, "sample_" + base)(I.SAMPLER_MODEL, xT.clone(), sig, **okw)
+    seen = []
+    out = getattr(K.sampling, "sample_" + base)(I.SAMPLER_MODEL, xT.cuda(), sig.cuda(), disable=True,
+                                                callback=lambda d: seen.append((d["i"], float(d["sigma_hat"]))), **pkw).cpu()
+    assert [s[0] for s in seen] == list(range(I.SAMPLER_N))
+    scale = ref.abs().max().item()
+    e_or = (out - ref).abs().max().item()
+    e_ref = np.abs(out.numpy() - golden_samplers["sampler." + name]).max()
+    print(f"{name}: max err vs oracle {e_or:.3e}, vs reference output {e_ref:.3e} (scale {scale:.3f})")
+    assert e_or < 2e-5 * scale and e_ref < 2e-5 * scale
+
+
+def test_extra_schedules_and_lincomb3(golden_samplers):
+    """Schedules against the reference's outputs; kdip_lincomb3 bit-exact against separately rounded torch arithmetic."""
+    import k_diffusion as K
+    from kdip import ops
+    assert np.allclose(K.sampling.get_sigmas_exponential(12, 0.02, 50.).numpy(), golden_samplers["sched.exponential"], rtol=1e-6, atol=0)
+    assert np.allclose(K.sampling.get_sigmas_polyexponential(12, 0.02, 50., rho=2.).numpy(), golden_samplers["sched.polyexponential"], rtol=1e-6, atol=0)
+    assert np.allclose(K.sampling.get_sigmas_vp(12).numpy(), golden_samplers["sched.vp"], rtol=1e-6, atol=0)
+    g = torch.Generator().manual_seed(4)
+    x, y, z = (torch.randn(2, 3, 16, 20, generator=g) for _ in range(3))
+    a, b, c = np.float32(0.7312), np.float32(-1.25e-3), np.float32(3.3)
+    ta, tb, tc = (torch.tensor(v) for v in (a, b, c))
+    assert torch.equal(ops.lincomb3(x.cuda(), a).cpu(), ta * x)
+    assert torch.equal(ops.lincomb3(x.cuda(), a, y.cuda(), b).cpu(), ta * x + tb * y)
+    assert torch.equal(ops.lincomb3(x.cuda(), a, y.cuda(), b, z.cuda(), c).cpu(), (ta * x + tb * y) + tc * z)
+    xc = x.cuda()
+    assert ops.lincomb3(xc, 1.0, y.cuda(), b, out=xc) is xc and torch.equal(xc.cpu(), x + tb * y)      # in place
+    with pytest.raises(ValueError):
+        ops.lincomb3(torch.zeros(6, device="cuda"), 1.0)                                               # n % 4 != 0

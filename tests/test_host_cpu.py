@@ -214,3 +214,28 @@ def test_stsl_host_composition_against_reference_golden(case, golden_stsl, monke
         err = (hat - ref).abs().max().item()
         assert err < 2e-3, (key, err)
     assert (torch.from_numpy(golden_stsl[f"stsl.{opname}.{sigma}"]) - ref).norm() / ref.norm() > 0.05   # the probes matter
+
+
+def test_extra_sampler_host_coefficients():
+    """Host-side fp32 coefficient helpers of the remaining samplers (k_diffusion/sampling.py of this package) against the oracle's
+    0-dim tensor arithmetic (itself pinned to the reference's outputs in test_oracle_golden.py): ancestral step, geometric
+    midpoint, linear-multistep coefficients."""
+    import k_diffusion as K
+    from oracle import sampler_ref
+    sig = sampler_ref.get_sigmas_karras(10, 0.05, 20.0)
+    hs = sig.numpy()
+    for i in range(10):
+        for eta in (1.0, 0.5, 0.0):
+            d_ref, u_ref = sampler_ref.ancestral_step(sig[i], sig[i + 1], eta)
+            d, u = K.sampling.get_ancestral_step(hs[i], hs[i + 1], eta)
+            assert abs(float(d) - float(d_ref)) <= 1e-6 * max(1.0, float(d_ref)) and abs(float(u) - float(u_ref)) <= 1e-6 * max(1.0, float(u_ref))
+        if sig[i + 1] > 0:
+            mid_ref = float(sig[i].log().lerp(sig[i + 1].log(), 0.5).exp())
+            assert abs(float(K.sampling._log_midpoint(hs[i], hs[i + 1])) - mid_ref) <= 2e-7 * mid_ref
+        cur = min(i + 1, 4)
+        for j in range(cur):
+            assert K.sampling.linear_multistep_coeff(cur, hs, i, j) == pytest.approx(sampler_ref.lms_coefficient(cur, hs, i, j), rel=1e-9)
+    with pytest.raises(ValueError):
+        K.sampling.linear_multistep_coeff(4, hs, 1, 0)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        K.sampling.sample_dpmpp_2m(lambda x, s: x, torch.zeros(1, 3, 8, 8), sig)
