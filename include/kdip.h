@@ -33,6 +33,9 @@ const char* kdip_last_error(void);
 int kdip_version(void);
 /* Number of CUDA kernels this library has launched in the process so far (bench.py reports the delta as gpu_launches). */
 unsigned long long kdip_launch_count(void);
+/* A caller that replays a captured CUDA graph of library calls bypasses the library's own launch path: it reports the kernel
+ * nodes of each replay here (the count kdip_launch_count advanced by while the graph was captured). */
+void kdip_launch_count_add(size_t n);
 /* Device sanity: returns KDIP_OK when the current device is sm_100 (B200); fills sm_count if non-null. */
 int kdip_device_check(int* sm_count);
 

@@ -85,6 +85,7 @@ int encode_tmap_bf16_2d(CUtensorMap* m, const void* base, uint64_t cols, uint64_
 extern "C" const char* kdip_last_error(void) { return kdip::g_err; }
 extern "C" int kdip_version(void) { return 1; }
 extern "C" unsigned long long kdip_launch_count(void) { return kdip::g_launches.load(std::memory_order_relaxed); }
+extern "C" void kdip_launch_count_add(size_t n) { kdip::g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 
 extern "C" int kdip_device_check(int* sm_count) {
   int dev = 0;

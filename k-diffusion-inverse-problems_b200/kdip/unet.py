@@ -103,9 +103,10 @@ class UNetEngine:
                 cur.wait_stream(side)
                 torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
+                n0 = lib.kdip_launch_count()
                 with torch.cuda.graph(g):
                     launch_fn(bufs)
-                r["graph"], r["bufs"] = g, bufs
+                r["graph"], r["bufs"], r["kernels"] = g, bufs, int(lib.kdip_launch_count() - n0)   # kernel nodes per replay
             except Exception as e:                        # noqa: BLE001 - eager launches remain fully functional
                 import warnings
                 warnings.warn(f"kdip: CUDA-graph capture of {key} failed ({e}); using eager launches")
@@ -144,6 +145,7 @@ class UNetEngine:
                 b["xs"].copy_(x_scale)
             check(lib.kdip_unet_prepare(self._h, N, ws, ws_bytes))   # the replay bypasses the library: keep its (N, workspace) current
             r["graph"].replay()
+            lib.kdip_launch_count_add(r["kernels"])
             out.copy_(b["out"])
             if want_cov:
                 cov.copy_(b["cov"])
@@ -199,6 +201,7 @@ class UNetEngine:
             r["bufs"]["seed"].copy_(seed)
             check(lib.kdip_unet_prepare(self._h, N, ws, ws_bytes))
             r["graph"].replay()
+            lib.kdip_launch_count_add(r["kernels"])
             out.copy_(r["bufs"]["grad"])
         else:
             check(lib.kdip_unet_vjp(self._h, ptr(seed), N, ptr(out), ws, ws_bytes, stream_ptr()))
