@@ -10,100 +10,96 @@ from . import sampling, utils
 
 
 class DiscreteSchedule(nn.Module):
-    """external.py:42-85."""
+    """The DDPM noise levels as a table: sigma <-> (fractional) timestep by piecewise-linear interpolation in log sigma
+    (external.py:42-85).  Buffers ``sigmas`` / ``log_sigmas`` keep the reference's names (they are in its checkpoints)."""
 
     def __init__(self, sigmas, quantize):
         super().__init__()
+        self.quantize = quantize
         self.register_buffer('sigmas', sigmas)
         self.register_buffer('log_sigmas', sigmas.log())
-        self.quantize = quantize
         self._log_sigmas_host = self.log_sigmas.detach().cpu().numpy().astype(np.float32)
 
-    @property
-    def sigma_min(self):
-        return self.sigmas[0]
-
-    @property
-    def sigma_max(self):
-        return self.sigmas[-1]
+    sigma_min = property(lambda self: self.sigmas[0])
+    sigma_max = property(lambda self: self.sigmas[-1])
 
     def get_sigmas(self, n=None):
-        if n is None:
-            return sampling.append_zero(self.sigmas.flip(0))
-        t_max = len(self.sigmas) - 1
-        t = torch.linspace(t_max, 0, n, device=self.sigmas.device)
-        return sampling.append_zero(self.t_to_sigma(t))
+        """All table entries from the noisiest down (n is None) or n levels evenly spaced in t, zero-terminated (:57-62)."""
+        if n is not None:
+            steps = torch.linspace(len(self.sigmas) - 1, 0, n, device=self.sigmas.device)
+            return sampling.append_zero(self.t_to_sigma(steps))
+        return sampling.append_zero(self.sigmas.flip(0))
+
+    def _bracket(self, log_sigma):
+        """Index of the last table entry <= log_sigma (0 when there is none), capped so that index + 1 exists: what the
+        reference's ``dists.ge(0).cumsum(0).argmax(0).clamp(max=n-2)`` selects on the ascending table (:71)."""
+        below = (log_sigma.reshape(1, -1) >= self.log_sigmas[:, None]).sum(dim=0)
+        return (below - 1).clamp(min=0, max=self.log_sigmas.shape[0] - 2)
 
     def sigma_to_t(self, sigma, quantize=None):
-        quantize = self.quantize if quantize is None else quantize
+        """Nearest table index (quantize) or the interpolated fractional index (:67-79)."""
         log_sigma = sigma.log()
-        dists = log_sigma - self.log_sigmas[:, None]
-        if quantize:
-            return dists.abs().argmin(dim=0).view(sigma.shape)
-        low_idx = dists.ge(0).cumsum(dim=0).argmax(dim=0).clamp(max=self.log_sigmas.shape[0] - 2)
-        high_idx = low_idx + 1
-        low, high = self.log_sigmas[low_idx], self.log_sigmas[high_idx]
-        w = ((low - log_sigma) / (low - high)).clamp(0, 1)
-        t = (1 - w) * low_idx + w * high_idx
-        return t.view(sigma.shape)
+        if self.quantize if quantize is None else quantize:
+            return (log_sigma.reshape(1, -1) - self.log_sigmas[:, None]).abs().argmin(dim=0).view(sigma.shape)
+        lo = self._bracket(log_sigma)
+        ls_lo, ls_hi = self.log_sigmas[lo], self.log_sigmas[lo + 1]
+        w = ((ls_lo - log_sigma.reshape(-1)) / (ls_lo - ls_hi)).clamp(0, 1)
+        return ((1 - w) * lo + w * (lo + 1)).view(sigma.shape)
 
     def sigma_to_t_host(self, sigma):
-        """Same piecewise-linear inverse evaluated on the host in fp32 (no device work, no sync): sigma float -> t float."""
-        ls = self._log_sigmas_host
+        """The same inverse evaluated on the host in fp32 (no device work, no sync): sigma float -> t float."""
+        table = self._log_sigmas_host
         with np.errstate(divide='ignore'):          # sigma = 0 (analytic_variance.py evaluates the trailing 0): log -> -inf, t -> 0
             log_sigma = np.log(np.float32(sigma))
-        low_idx = min(int(np.count_nonzero(log_sigma - ls >= 0)) - 1, len(ls) - 2)
-        if np.count_nonzero(log_sigma - ls >= 0) == 0:
-            low_idx = 0   # cumsum().argmax() of an all-False column is 0
-        high_idx = low_idx + 1
-        low, high = ls[low_idx], ls[high_idx]
-        w = np.float32(np.clip((low - log_sigma) / (low - high), 0, 1))
-        return float(np.float32((np.float32(1) - w) * np.float32(low_idx) + w * np.float32(high_idx)))
+        lo = min(max(int(np.count_nonzero(log_sigma >= table)) - 1, 0), len(table) - 2)
+        w = np.float32(np.clip((table[lo] - log_sigma) / (table[lo] - table[lo + 1]), 0, 1))
+        return float(np.float32((np.float32(1) - w) * np.float32(lo) + w * np.float32(lo + 1)))
 
     def t_to_sigma(self, t):
+        """Interpolate log sigma between the two neighbouring integer timesteps (:81-85)."""
         t = t.float()
-        low_idx, high_idx, w = t.floor().long(), t.ceil().long(), t.frac()
-        log_sigma = (1 - w) * self.log_sigmas[low_idx] + w * self.log_sigmas[high_idx]
-        return log_sigma.exp()
+        frac = t.frac()
+        return ((1 - frac) * self.log_sigmas[t.floor().long()] + frac * self.log_sigmas[t.ceil().long()]).exp()
 
 
 class DiscreteEpsDDPMDenoiser(DiscreteSchedule):
-    """external.py:88-115 (forward only; the training loss is out of scope)."""
+    """An eps-prediction DDPM model seen as a Karras denoiser: D(x, sigma) = x - sigma * eps(x / sqrt(sigma^2 + 1), t(sigma))
+    (external.py:88-115; forward only, the training loss is out of scope)."""
+
+    sigma_data = 1.
 
     def __init__(self, model, alphas_cumprod, quantize):
         super().__init__(((1 - alphas_cumprod) / alphas_cumprod) ** 0.5, quantize)
         self.inner_model = model
-        self.sigma_data = 1.
 
     def get_scalings(self, sigma):
-        c_out = -sigma
-        c_in = 1 / (sigma ** 2 + self.sigma_data ** 2) ** 0.5
-        return c_out, c_in
+        """(c_out, c_in) of :97-100."""
+        return -sigma, 1 / (sigma ** 2 + self.sigma_data ** 2) ** 0.5
 
     def get_eps(self, *args, **kwargs):
         return self.inner_model(*args, **kwargs)
 
     def forward(self, input, sigma, **kwargs):
-        c_out, c_in = [utils.append_dims(x, input.ndim) for x in self.get_scalings(sigma)]
-        eps = self.get_eps(input * c_in, self.sigma_to_t(sigma), **kwargs)
-        return input + eps * c_out
+        c_out, c_in = (utils.append_dims(c, input.ndim) for c in self.get_scalings(sigma))
+        return input + c_out * self.get_eps(input * c_in, self.sigma_to_t(sigma), **kwargs)
+
+
+def _alphas_cumprod(diffusion, device):
+    return torch.tensor(diffusion.alphas_cumprod, device=device, dtype=torch.float32)
 
 
 class OpenAIDenoiser(DiscreteEpsDDPMDenoiser):
-    """external.py:117-132."""
+    """Wrapper for the guided-diffusion UNets, which emit (eps, variance interpolation) on 6 channels (external.py:117-132)."""
 
     def __init__(self, model, diffusion, quantize=False, has_learned_sigmas=True, device='cpu'):
-        alphas_cumprod = torch.tensor(diffusion.alphas_cumprod, device=device, dtype=torch.float32)
-        super().__init__(model, alphas_cumprod, quantize=quantize)
+        super().__init__(model, _alphas_cumprod(diffusion, device), quantize=quantize)
         self.has_learned_sigmas = has_learned_sigmas
 
     def get_eps(self, *args, **kwargs):
-        model_output = self.inner_model(*args, **kwargs)
-        if self.has_learned_sigmas:
-            if kwargs.get('return_variance', False):
-                return model_output
-            return model_output.chunk(2, dim=1)[0]
-        return model_output
+        out = self.inner_model(*args, **kwargs)
+        if not self.has_learned_sigmas or kwargs.get('return_variance', False):
+            return out
+        return out.chunk(2, dim=1)[0]
 
 
 class OpenAIDenoiserV2(DiscreteEpsDDPMDenoiser):
@@ -112,8 +108,7 @@ class OpenAIDenoiserV2(DiscreteEpsDDPMDenoiser):
 
     def __init__(self, model, diffusion, quantize=False, device='cpu', ortho_tf_type=None):
         from condition.utils import OrthoTransform
-        alphas_cumprod = torch.tensor(diffusion.alphas_cumprod, device=device, dtype=torch.float32)
-        super().__init__(model, alphas_cumprod, quantize=quantize)
+        super().__init__(model, _alphas_cumprod(diffusion, device), quantize=quantize)
         self.out_cov = nn.Conv2d(model.model_channels * int(model.channel_mult[0]), 2 * 3, 1)
         self.ortho_tf_type = ortho_tf_type
         self.ortho_tf = OrthoTransform(ortho_tf_type)
