@@ -103,7 +103,7 @@ def test_groupnorm_forward_backward(C0, C1, rs, silu, film):
 
 
 @pytest.mark.parametrize("T,heads,N", [(64, 1, 2), (64, 8, 3), (128, 2, 3), (256, 3, 2), (256, 8, 1), (1024, 2, 1),
-                                         (384, 2, 2), (512, 3, 1), (1024, 8, 2)])   # T >= 384: streamed-block tcgen05 kernels
+                                         (384, 2, 2), (512, 3, 1), (1024, 8, 2), (2048, 1, 1)])   # T >= 384: streamed-block tcgen05 kernels
 def test_attention_forward_backward(T, heads, N):
     """QKVAttentionLegacy (unet.py:339-356): per-head interleaved [q,k,v], scale ch^-1/4 on q and k, fp32 softmax."""
     from kdip._lib import check, lib, ptr, stream_ptr
