@@ -138,3 +138,67 @@ def test_lightning_checkpoint_end_to_end(tmp_path, golden_v2):
     e_lv = ((lvo.cpu() - ref_lvo).norm() / ref_lvo.norm()).item()
     print(f"checkpoint -> v2 denoiser: model_output rel-L2 {e_mo:.3e}, logvar_ot rel-L2 {e_lv:.3e}")
     assert e_mo < 1.5e-2 and e_lv < 1.5e-2
+
+
+def test_sample_script_flow(tmp_path):
+    """The main body of sample_condition_openai.py:112-210 executed on this package, end to end on files: OpenAI ``.pt`` checkpoint
+    -> ``create_model_and_diffusion`` + ``load_state_dict(dist_util.load_state_dict(...))``; image folder -> ``FolderOfImages``
+    (batched GPU decode); ``get_operator`` -> measurement; ``ConditionOpenAIDenoiser`` -> ``sample_heun`` driven by
+    ``K.evaluation.compute_features``; PSNR / SSIM; ``to_pil_image(...).save``.  Structural checks only: 4-step trajectories of the
+    synthetic tiny UNet are chaotic (module docstring of test_guidance_gpu.py); numerical parity of every stage is pinned by the
+    other tests."""
+    from PIL import Image
+    import k_diffusion as K
+    from condition.condition import ConditionOpenAIDenoiser
+    from condition.measurements import get_operator
+    from kdip import checkpoint, ops
+    from kdip.data import ImageBatchLoader
+    from kdip.dist import Accelerator
+    from oracle import metrics_ref, unet_ref
+    root = str(tmp_path)
+    ckpt = os.path.join(root, "tiny.pt")
+    torch.save(unet_ref.init_state_dict(unet_ref.tiny_config(), seed=0), ckpt)
+    os.makedirs(os.path.join(root, "images"))
+    truth = I.image(64, batch=3, seed=1)
+    for i in range(3):
+        K.utils.to_pil_image(truth[i:i + 1]).save(os.path.join(root, "images", f"{i:05d}.png"))
+    config = {"model": {"openai": {"image_size": 64, "num_channels": 64, "num_res_blocks": 1, "attention_resolutions": "16,8",
+                                   "channel_mult": "1,2,3,4"}, "sigma_min": 0.01, "sigma_max": 80.0},
+              "dataset": {"location": os.path.join(root, "images")},
+              "operator": {"name": "gaussian_blur", "in_shape": (1, 3, 64, 64), "kernel_size": 61, "intensity": 3.0, "sigma_s": 0.05}}
+    accelerator = Accelerator()
+    device = accelerator.device
+    inner_model, diffusion = checkpoint.load_openai_unet(ckpt, config["model"]["openai"], device=device)
+    operator = get_operator(device=device, **config["operator"])
+    sigmas = K.sampling.get_sigmas_karras(4, config["model"]["sigma_min"], config["model"]["sigma_max"], rho=7., device=device)
+    test_set = K.utils.FolderOfImages(config["dataset"]["location"])
+    assert len(test_set) == 3
+    hats, x0s, seen = [], [], 0
+    for (x0,) in ImageBatchLoader(test_set, batch_size=2, device=device):          # batches of 2 and 1
+        b = x0.shape[0]
+        measurement = operator.forward(x0, flatten=True)
+        assert measurement[0].shape == x0.shape and measurement[1].shape == (b, x0[0].numel())
+        model = ConditionOpenAIDenoiser(inner_model=inner_model, diffusion=diffusion, x0_cov_type="convert", recon_mse=None,
+                                        operator=operator, measurement=measurement, guidance="I", device=device,
+                                        mle_sigma_thres=0.2).eval()
+
+        def sample_fn(n):
+            x = torch.randn([n, 3, 64, 64], device=device) * config["model"]["sigma_max"]
+            return K.sampling.sample_heun(model, x, sigmas, disable=True)
+
+        hat = K.evaluation.compute_features(accelerator, sample_fn, lambda x: x, b, b)
+        assert hat.shape == x0.shape and torch.isfinite(hat).all() and hat.abs().max() <= 1.0 + 1e-5
+        hats.append(hat)
+        x0s.append(x0)
+        seen += b
+    assert seen == 3
+    hat, x0 = torch.cat(hats), torch.cat(x0s)
+    assert torch.equal(x0.cpu(), torch.stack([metrics_ref.to_tensor_pm1(metrics_ref.to_u8(truth[i])) for i in range(3)]))   # decode
+    psnr, ssim = ops.psnr(x0, hat).cpu(), ops.ssim(x0, hat).cpu()
+    assert psnr.shape == (3,) and torch.isfinite(psnr).all() and torch.isfinite(ssim).all() and (ssim.abs() <= 1.0 + 1e-9).all()
+    for i in range(3):
+        assert abs(psnr[i].item() - metrics_ref.psnr(x0[i].cpu(), hat[i].cpu())) < 1e-6
+        path = os.path.join(root, f"hat_{i:05d}.png")
+        K.utils.to_pil_image(hat[i:i + 1]).save(path)
+        assert np.array_equal(np.asarray(Image.open(path)), metrics_ref.to_u8(hat[i].cpu()))
+    print("sample flow: psnr", [round(v, 2) for v in psnr.tolist()], "ssim", [round(v, 3) for v in ssim.tolist()])
