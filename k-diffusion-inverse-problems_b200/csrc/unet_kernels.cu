@@ -93,23 +93,31 @@ __global__ void gn_finalize_kernel(const float* __restrict__ st0, int C0, const 
   const int n = blockIdx.x;
   const int C = C0 + C1;
   const int cpg = C / 32;
-  if (threadIdx.x < 32) {
-    const int g = threadIdx.x;
+  {
+    // 256 threads = 32 groups x 8 lanes: each lane sums every 8th channel of its group, then an 8-lane butterfly
+    const int g = threadIdx.x >> 3, l = threadIdx.x & 7;
     double S1 = 0.0, S2 = 0.0;
-    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+    for (int c = g * cpg + l; c < (g + 1) * cpg; c += 8) {
       const float* p = (c < C0) ? st0 + ((size_t)n * C0 + c) * 2 : st1 + ((size_t)n * C1 + (c - C0)) * 2;
       S1 += (double)p[0];
       S2 += (double)p[1];
     }
-    const double cnt = (double)cpg * (double)P;
-    const double mean = S1 / cnt;
-    double var = S2 / cnt - mean * mean;
-    if (var < 0.0) var = 0.0;
-    const float rstd = (float)(1.0 / sqrt(var + (double)kGnEps));
-    g_mean[g] = (float)mean;
-    g_rstd[g] = rstd;
-    mr[((size_t)n * 32 + g) * 2] = (float)mean;
-    mr[((size_t)n * 32 + g) * 2 + 1] = rstd;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      S1 += __shfl_xor_sync(0xffffffffu, S1, o);
+      S2 += __shfl_xor_sync(0xffffffffu, S2, o);
+    }
+    if (l == 0) {
+      const double cnt = (double)cpg * (double)P;
+      const double mean = S1 / cnt;
+      double var = S2 / cnt - mean * mean;
+      if (var < 0.0) var = 0.0;
+      const float rstd = (float)(1.0 / sqrt(var + (double)kGnEps));
+      g_mean[g] = (float)mean;
+      g_rstd[g] = rstd;
+      mr[((size_t)n * 32 + g) * 2] = (float)mean;
+      mr[((size_t)n * 32 + g) * 2 + 1] = rstd;
+    }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -476,19 +484,26 @@ __global__ void gn_bwd_finalize_kernel(const float* __restrict__ red, const floa
   __shared__ float c1s[32], c2s[32];
   const int n = blockIdx.x;
   const int cpg = C / 32;
-  if (threadIdx.x < 32) {
-    const int g = threadIdx.x;
+  {
+    const int g = threadIdx.x >> 3, l = threadIdx.x & 7;     // 32 groups x 8 lanes, as in gn_finalize_kernel
     const float mean = mr[((size_t)n * 32 + g) * 2], rstd = mr[((size_t)n * 32 + g) * 2 + 1];
     double a1 = 0.0, a2 = 0.0;
-    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+    for (int c = g * cpg + l; c < (g + 1) * cpg; c += 8) {
       const double w = (double)ab[((size_t)n * C + c) * 2] / (double)rstd;   // gamma*(1+scale)
       const double R1 = red[((size_t)n * C + c) * 2], R2 = red[((size_t)n * C + c) * 2 + 1];
       a1 += w * R1;
       a2 += w * (double)rstd * (R2 - (double)mean * R1);                      // sum g_xhat * xhat
     }
-    const double m = (double)cpg * (double)P;
-    c1s[g] = (float)(a1 / m);
-    c2s[g] = (float)(a2 / m);
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+      a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    }
+    if (l == 0) {
+      const double m = (double)cpg * (double)P;
+      c1s[g] = (float)(a1 / m);
+      c2s[g] = (float)(a2 / m);
+    }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
