@@ -58,4 +58,4 @@ for ot in ("dwt", "dct"):
     op = get_operator(device=dev, name="gaussian_blur", in_shape=(1, 3, 256, 256), kernel_size=61, intensity=3.0, sigma_s=0.05)
     y = op.forward(x0, flatten=True)
     cm = ConditionOpenAIDenoiserV2(denoiser=den, operator=op, measurement=y, guidance="II", device=dev, mle_sigma_thres=1.0, ortho_tf_type=ot).eval()
-    print(f"{'cfg5 v2 gaussian deblur / II ' + ot:36s}: sigma 1.5 {timed(cm, 1.5):7.2f} ms   sigma 0.5 {timed(cm, 0.5):7.2f} ms   (B={B}, UNet forward only) cg_iters={getattr(cm, 'last_cg_iters', None)}", flush=True)
+    print(f"{'cfg5 v2 gaussian deblur / II ' + ot:36s}: sigma 1.5 {timed(cm, 1.5):7.2f} ms   sigma 0.5 {timed(cm, 0.5):7.2f} ms   (B={B}, UNet forward only) cg_iters={max(getattr(op.handle, 'last_cg_iters', None) or [0])}", flush=True)

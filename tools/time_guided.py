@@ -35,7 +35,7 @@ for guidance, cov in (("I", "convert"), ("pgdm", "pgdm")):
             cm(xt, sg)
         e1.record()
         torch.cuda.synchronize()
-        extra = getattr(cm, "last_cg_iters", None)
+        extra = getattr(getattr(cm.operator, "handle", None), "last_cg_iters", None)
         print(f"guidance={guidance} cov={cov} sigma={sigma}: {e0.elapsed_time(e1)/iters:.2f} ms per guided eval (B={B}) cg_iters={extra}", flush=True)
 eng = model.engine()
 xs = torch.randn(B, 3, 256, 256, device=dev); tt = torch.full((B,), 338.0, device=dev); sd6 = torch.randn(B, 6, 256, 256, device=dev)
