@@ -250,3 +250,49 @@ def test_extra_sampler_host_coefficients():
         K.sampling.linear_multistep_coeff(4, hs, 1, 0)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         K.sampling.sample_dpmpp_2m(lambda x, s: x, torch.zeros(1, 3, 8, 8), sig)
+
+
+@pytest.mark.parametrize("case", I.EXTRA_SAMPLER_CASES, ids=lambda c: c[0])
+def test_extra_sampler_host_loops_against_reference_golden(case, golden_samplers, monkeypatch):
+    """Host side of the remaining samplers (step coefficients, branch decisions, noise / callback plumbing) against the
+    REFERENCE's own outputs, with the three update kernels replaced by torch stand-ins that exist only in this test (the
+    product has no CPU path; the kernels themselves are checked on the GPU in test_guidance_gpu.py::test_extra_samplers)."""
+    import k_diffusion as K
+    from kdip import ops
+    from oracle import sampler_ref
+    f32 = lambda v: torch.tensor(np.float32(v))
+
+    def lincomb3(x, a, y=None, b=0.0, z=None, c=0.0, out=None):
+        r = f32(a) * x
+        if y is not None:
+            r = r + f32(b) * y
+        if z is not None:
+            r = r + f32(c) * z
+        return r if out is None else out.copy_(r)
+
+    def euler_step(x, denoised, sigma_hat, dt, want_d=False):
+        d = (x - denoised) / f32(sigma_hat)
+        return (x + d * f32(dt), d) if want_d else x + d * f32(dt)
+
+    def churn_(x, eps, s_noise, sigma, sigma_hat):
+        return x + eps * f32(s_noise) * f32(np.sqrt(np.float32(sigma_hat) ** 2 - np.float32(sigma) ** 2))
+
+    monkeypatch.setattr(ops, "lincomb3", lincomb3)
+    monkeypatch.setattr(ops, "euler_step", euler_step)
+    monkeypatch.setattr(ops, "churn_", churn_)
+    monkeypatch.setattr(K.sampling, "_prep", lambda x: x.detach().contiguous().float())
+    name, kw = case
+    base = name.split("/")[0]
+    noises, sig = I.sampler_noises(), sampler_ref.get_sigmas_karras(I.SAMPLER_N, I.SAMPLER_SIGMA_MIN, I.SAMPLER_SIGMA_MAX)
+    kw = dict(kw)
+    if "ancestral" in name:
+        by_sigma = {float(s): k for k, s in enumerate(sig[:-1])}
+        kw["noise_sampler"] = lambda s, s_next: noises[by_sigma[float(s)]]
+    elif base == "dpm_2":
+        kw["noise_sampler"] = lambda i, x: noises[i]
+    seen = []
+    out = getattr(K.sampling, "sample_" + base)(I.SAMPLER_MODEL, I.sampler_start(), sig, disable=True,
+                                                callback=lambda d: seen.append(d["i"]), **kw)
+    ref = golden_samplers["sampler." + name]
+    assert seen == list(range(I.SAMPLER_N))
+    assert np.abs(out.numpy() - ref).max() <= 2e-6 * np.abs(ref).max()
