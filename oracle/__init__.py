@@ -2,9 +2,11 @@
 
 This package is a plain torch-CPU / numpy fp32 restatement of the reference algorithm
 (xypeng9903/k-diffusion-inverse-problems @ d5ae606).  Every function cites the reference
-file:line it follows.  It is imported only by ``tests/``, ``__graft_entry__.smoke()`` and the
-``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` — never by the product package
-(``k-diffusion-inverse-problems_b200/``), which must fail loudly when the CUDA library is missing.
+file:line it follows.  It is imported only by ``tests/`` (including the developer scripts under
+``tests/tools/``), ``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference`` legs of
+``bench.py`` — never by the product package (``k-diffusion-inverse-problems_b200/``) nor by the measurement
+scripts under ``tools/``; the product must fail loudly when the CUDA library is missing
+(``tests/test_host_cpu.py::test_no_cpu_fallback`` enforces both).
 
 Pinning: the reference ships no tests or golden vectors, so the oracle is pinned
 against outputs of the reference's own code executed in the build container

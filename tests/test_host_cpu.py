@@ -133,6 +133,10 @@ def test_no_cpu_fallback():
                 checked += 1
                 assert "import oracle" not in text and "from oracle" not in text, f"{f}: the product must not import the oracle"
     assert checked > 20
+    for f in os.listdir(os.path.join(ROOT, "tools")):        # the measurement scripts use the product package alone
+        if f.endswith(".py"):
+            text = open(os.path.join(ROOT, "tools", f)).read()
+            assert "import oracle" not in text and "from oracle" not in text, f"tools/{f} must not import the oracle"
 
 
 _WORKER = r'''

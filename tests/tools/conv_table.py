@@ -1,6 +1,6 @@
 """Offline: pair the conv launches of an ncu launch list (tools/time_unet.py run) with the FFHQ UNet's conv shapes."""
 import csv, sys, os
-sys.path[:0] = [os.path.dirname(os.path.dirname(os.path.abspath(__file__)))]
+sys.path[:0] = [os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))]
 from oracle import unet_ref
 path = sys.argv[1] if len(sys.argv) > 1 else 'gpurun_out/launches_unet.csv'
 N = int(sys.argv[2]) if len(sys.argv) > 2 else 32

@@ -1,6 +1,6 @@
 """GPU debug: tiny UNet input-VJP vs the fp32 oracle under several call patterns."""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "k-diffusion-inverse-problems_b200"), os.path.join(ROOT, "tests", "golden")]
 import torch
 import inputs as I

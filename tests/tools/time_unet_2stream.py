@@ -1,7 +1,7 @@
 """Experiment: one B-image UNet forward+VJP vs two concurrent half-batches on two CUDA streams (tensor-bound convs of one half
-overlap the HBM-bound GroupNorm passes of the other).  Usage: python tools/time_unet_2stream.py [B] [iters]"""
+overlap the HBM-bound GroupNorm passes of the other).  Usage: python tests/tools/time_unet_2stream.py [B] [iters]"""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "k-diffusion-inverse-problems_b200")]
 import torch
 from oracle import unet_ref

@@ -1,6 +1,6 @@
 """Experiment: UNet forward+VJP launched kernel by kernel vs replayed from a captured CUDA graph.  Usage: [B] [iters]"""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "k-diffusion-inverse-problems_b200")]
 import torch
 from oracle import unet_ref

@@ -1,5 +1,5 @@
 #!/bin/bash
-# A/B of the conv_gemm variants on the FFHQ UNet (B=32): per-launch device times via ncu, summarised by tools/conv_table.py
+# A/B of the conv_gemm variants on the FFHQ UNet (B=32): per-launch device times via ncu, summarised by tests/tools/conv_table.py
 mkdir -p gpurun_out
 KDIP_CONV_DEBUG=1 timeout 300 python tools/time_unet.py 32 3 > gpurun_out/ab_default_time.log 2> gpurun_out/ab_default_debug.log
 KDIP_CONV_PAIR=0 timeout 300 python tools/time_unet.py 32 3 > gpurun_out/ab_nopair_time.log 2>&1

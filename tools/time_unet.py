@@ -3,14 +3,17 @@ import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "k-diffusion-inverse-problems_b200")]
 import torch
-from oracle import unet_ref
-from kdip.unet import UNetEngine
+from condition.diffpir_utils.utils_model import create_argparser
+from guided_diffusion.script_util import args_to_dict, create_model_and_diffusion, model_and_diffusion_defaults
+from kdip.synth import synthetic_state_dict
 
+UNET_FWD_FLOPS = 387.93e9      # FFHQ UNet forward, per image (2 x MAC)
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 5
-cfg = unet_ref.ffhq_config()
-sd = unet_ref.init_state_dict(cfg, seed=0)
-eng = UNetEngine(sd)
+margs = create_argparser({"num_channels": 128, "num_res_blocks": 1, "attention_resolutions": "16"}).parse_args([])
+model, _ = create_model_and_diffusion(**args_to_dict(margs, model_and_diffusion_defaults().keys()))
+model.load_state_dict(synthetic_state_dict(model, seed=0))
+eng = model.eval().cuda().engine()
 print("workspace GB", eng.workspace_bytes(B) / 1e9)
 x = torch.randn(B, 3, 256, 256, device="cuda")
 t = torch.full((B,), 500.0, device="cuda")
@@ -27,5 +30,5 @@ for _ in range(iters):
     torch.cuda.synchronize()
     tf += e[0].elapsed_time(e[1]); tb += e[1].elapsed_time(e[2])
 tf /= iters; tb /= iters
-fl = unet_ref.unet_flops(cfg) * B
+fl = UNET_FWD_FLOPS * B
 print(f"B={B}: fwd {tf:.2f} ms ({fl/tf/1e9:.1f} TFLOP/s)  vjp {tb:.2f} ms ({fl/tb/1e9:.1f} TFLOP/s)  fwd+vjp {tf+tb:.2f} ms -> {B/(tf+tb)*1000/199:.3f} img/s @199 evals")
