@@ -49,12 +49,12 @@ int kdip_churn(float* x, const float* noise, float s_noise, float sigma, float s
 /* d = (x - denoised)/sigma_hat ; x_out = x + d*dt ; d_out may be NULL (Euler)          (sampling.py:129-134,170-179) */
 int kdip_euler_step(const float* x, const float* denoised, float sigma_hat, float dt, float* x_out, float* d_out,
                     size_t n, kdip_stream_t s);
-/* d2 = (x2 - denoised2)/sigma_next ; x_out = x + (d + d2)/2 * dt                       (sampling.py:180-183) */
 /* out = a*x + b*y + c*z, host scalars, products and sums rounded separately; y / z may be NULL; out may alias an input.
  * The state update of the remaining k_diffusion/sampling.py samplers (sample_euler_ancestral :139-156, sample_dpm_2 :187-215,
  * sample_dpm_2_ancestral :218-248, sample_lms :259-275, sample_dpmpp_2s_ancestral :507-538, sample_dpmpp_2m :583-606).       */
 int kdip_lincomb3(const float* x, const float* y, const float* z, float a, float b, float c, float* out, size_t n,
                   kdip_stream_t s);
+/* d2 = (x2 - denoised2)/sigma_next ; x_out = x + (d + d2)/2 * dt                       (sampling.py:180-183) */
 int kdip_heun_step(const float* x, const float* d, const float* x2, const float* denoised2, float sigma_next, float dt,
                    float* x_out, size_t n, kdip_stream_t s);
 
@@ -84,7 +84,9 @@ int kdip_pmv_epilogue(const float* unet_out, const float* x, const kdip_pmv_scal
                       int var_mode, int B, int HW, kdip_stream_t s);
 /* VJP seed for the UNet output given v = d(loss)/d(x0_mean): writes seed [B,6,HW] = (-recipm1*m*v, 0) with
  * m = 1 where the clamp is inactive (x0_mean strictly inside (-1,1) reproduces torch.clamp's gradient), and
- * direct [B,3,HW] = recip*c_in*m*v (the d/dx of the explicit recip*c_in*x term). */
+ * direct [B,3,HW] = recip*c_in*m*v (the d/dx of the explicit recip*c_in*x term; NULL to skip).
+ * x0_mean == NULL: no clamp (m = 1) - the v2 denoiser x0 = x - sigma*eps (condition/condition.py:287-291) with
+ * sc = {c_in 1, recip 1, recipm1 sigma}: seed = (-sigma*v, 0), direct = v. */
 int kdip_pmv_vjp_seed(const float* x0_mean, const float* v, const kdip_pmv_scalars* sc, float* seed,
                       float* direct, int B, int HW, kdip_stream_t s);
 
@@ -183,6 +185,12 @@ int kdip_op_forward(const kdip_op* op, const float* x, const float* noise, float
 /* operator.transpose(y): blur A^T y (conj OTF), SR ifft2(conj(FB) fft2(upsample(y))), inpainting identity
  *                                                                                       measurements.py:113-122,150-156,190-196,228-238 */
 int kdip_op_transpose(const kdip_op* op, const float* y, float* x, int B, void* ws, size_t ws_bytes, kdip_stream_t s);
+/* Adjoint of operator.forward(noiseless): what autograd computes in LinearOperator.auto_transpose (measurements.py:48-52) and in
+ * the DPS branch (condition.py:144-146).  g has y's shape.  Blur: conj OTF; SR: the Resizer's adjoint; inpainting: mask. */
+int kdip_op_forward_adjoint(const kdip_op* op, const float* g, float* x, int B, void* ws, size_t ws_bytes, kdip_stream_t s);
+/* fft2 over (H, W) of x [B,3,S,S] -> interleaved complex64 [B,3,S,S]: the torch.fft.fftn of utils_sisr.py:91-95 behind the FBFy
+ * member of operator.pre_calculated.  Spectral operators only. */
+int kdip_op_fft2(const kdip_op* op, const float* x, float* out_full, int B, void* ws, size_t ws_bytes, kdip_stream_t s);
 /* FB of pre_calculate (utils_sisr.py:79-96) as interleaved complex64 [S][S] (device), for operator.pre_calculated */
 int kdip_op_otf(const kdip_op* op, float* fb_full, kdip_stream_t s);
 /* closed-form mat for scalar x0 variance theta[b] (device, B floats)                   condition.py:322-323,356-357,408-410 */

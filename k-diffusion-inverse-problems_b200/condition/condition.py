@@ -88,6 +88,20 @@ class ConditionDenoiser(nn.Module):
         Returns the two terms (g wrt the scaled UNet input, direct) that kdip_guidance_combine sums."""
         raise NotImplementedError
 
+    def _data_grad(self, y, x0_mean):
+        """(A^T r [B,3,H,W], ||r||_2 [B]) with r = y - operator.forward(x0, noiseless=True) (condition.py:144-146).  Built-in
+        operators run kdip_dps_grad; an operator registered by the user without a kdip handle is differentiated through its own
+        torch ``forward``, exactly as the reference's autograd does."""
+        handle = getattr(self.operator, "handle", None)
+        if handle is not None:
+            return handle.dps_grad(y, x0_mean)
+        with torch.enable_grad():
+            x0 = x0_mean.detach().clone().requires_grad_()
+            r = y - self.operator.forward(x0, noiseless=True)
+            half_sq = 0.5 * r.pow(2).flatten(1).sum(1)
+            (g,) = torch.autograd.grad(half_sq.sum(), x0)
+        return (-g).contiguous().float(), (2.0 * half_sq.detach()).sqrt().float().contiguous()
+
     def _theta(self, x0_var, theta0_var):
         return x0_var if self.ortho_tf_type is None else theta0_var
 
@@ -123,7 +137,7 @@ class ConditionDenoiser(nn.Module):
         B = x.shape[0]
         sig = _uniform(_host_sigma(sigma, B))
         x0_mean = self.uncond_pred(x, sigma)[0]
-        v, norm = self.operator.handle.dps_grad(self._y_for(B), x0_mean)
+        v, norm = self._data_grad(self._y_for(B), x0_mean)
         g, direct = self._score(x0_mean, v)
         coef = float(np.float32(sig) ** 2 * np.float32(self.zeta)) / norm   # [B] device scalars: sigma^2 zeta / ||r_b||
         return ops.guidance_combine(x0_mean, g, direct, coef, self._ctx["c_in_dev"])
@@ -148,7 +162,7 @@ class ConditionDenoiser(nn.Module):
         one, w_dev, mw_dev = _dev([1.0] * B, x.device), _dev([w] * B, x.device), _dev([-w] * B, x.device)
         x0_mean = self.uncond_pred(x, sigma)[0]
         c_in_dev = self._ctx["c_in_dev"]
-        v, norm = self.operator.handle.dps_grad(self._y_for(B), x0_mean)       # A^T r, ||r|| per image
+        v, norm = self._data_grad(self._y_for(B), x0_mean)                     # A^T r, ||r|| per image
         eps = [self._hutchinson_eps(x).to(x.device, torch.float32).contiguous() for _ in range(n)]
         seed_vec = ops.lincomb(v, eps[0] if n else v, float(np.float32(self.zeta)) / norm, w_dev if n else _dev([0.0] * B, x.device))
         for k in range(1, n):
@@ -228,6 +242,9 @@ class ConditionOpenAIDenoiser(ConditionDenoiser):
         t_int = [int(self.denoiser.sigma_to_t_host(float(sig)))] * B                     # condition.py:233: .long() truncates
         tm = getattr(self.diffusion, "timestep_map", None)
         t_model = [tm[t] for t in t_int] if tm is not None else t_int                    # respace.py:123-128
+        if getattr(self.diffusion, "rescale_timesteps", False):                          # respace.py:125-126 / gaussian_diffusion.py:254
+            orig = getattr(self.diffusion, "original_num_steps", self.diffusion.num_timesteps)
+            t_model = [float(t) * (1000.0 / orig) for t in t_model]
         c_in_dev = _dev(c_in, x.device)
         eng = self.inner_model.engine()
         out = eng.forward(x, _dev([float(t) for t in t_model], x.device), x_scale=c_in_dev)
@@ -288,11 +305,20 @@ class ConditionOpenAIDenoiserV2(ConditionDenoiser):
         x0_mean, x0_var, theta0_var = ops.v2_epilogue(out, cov, x, _dev(sig_list, x.device), want_var=mle)
         if not mle:
             x0_var = theta0_var = _dev([float(sig ** 2 / (1 + sig ** 2))] * B, x.device)
-        self._ctx = None
+        eng = self.denoiser.inner_model.engine()
+        c_in = [float(np.float32(1) / np.sqrt(sig * sig + np.float32(1)))] * B
+        self._ctx = dict(eng=eng, token=eng.forward_token, c_in_dev=_dev(c_in, x.device),
+                         sc=ops.v2_vjp_scalars(sig_list, x.device))
         return x0_mean, x0_var, theta0_var
 
     def _score(self, x0_mean, v):
-        raise NotImplementedError("the v2 (DWT-Var) denoiser is used with VJP-free guidance (type II / DiffPIR) on this path")
+        """x0 = x - sigma * eps(c_in x, t) is unclamped (condition.py:287-291): seed (-sigma v, 0) on the UNet's 6 output channels
+        (the out_cov head does not enter x0_mean), direct term v."""
+        c = self._ctx
+        if c["eng"].forward_token != c["token"]:
+            raise RuntimeError("the UNet engine ran another forward since uncond_pred; its saved activations are gone")
+        seed, direct = ops.pmv_vjp_seed(None, v, c["sc"], like=x0_mean)
+        return c["eng"].vjp(seed), direct
 
 
 # ---------------------------------------------

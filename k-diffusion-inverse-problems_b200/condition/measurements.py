@@ -43,10 +43,42 @@ def get_operator(name: str, **kwargs):
     return __OPERATOR__[name](**kwargs)
 
 
+class _ForwardFn(torch.autograd.Function):
+    """operator.forward as an autograd node: the backward is the adjoint of the SAME forward (kdip_op_forward_adjoint), which is
+    what torch.autograd derives in the reference (auto_transpose, measurements.py:48-52; DPS, condition.py:144-146)."""
+
+    @staticmethod
+    def forward(ctx, x, handle, noise):
+        ctx.handle = handle
+        return handle.forward(x, noise)
+
+    @staticmethod
+    def backward(ctx, g):
+        return ctx.handle.forward_adjoint(g.contiguous()), None, None
+
+
+def _apply_forward(handle, data, noise):
+    if torch.is_grad_enabled() and data.requires_grad:
+        return _ForwardFn.apply(data, handle, noise)
+    return handle.forward(data, noise)
+
+
 class LinearOperator(ABC):
     @abstractmethod
     def forward(self, data, flatten=False, noiseless=False):
         raise NotImplementedError("The class {} requires a forward function!".format(self.__class__.__name__))
+
+    def auto_transpose(self, y, flatten=False):
+        """measurements.py:48-52: the VJP of ``forward`` (noiseless) at a random point - for a linear operator its exact adjoint.
+        Works for the built-in operators (their forward is an autograd node over the CUDA adjoint kernels) and for any
+        user-registered operator whose forward is written in torch."""
+        with torch.enable_grad():
+            input = torch.randn(y.shape[0], *self.in_shape[-3:]).to(self.device).requires_grad_()
+            out = self.forward(input, flatten=flatten, noiseless=True)
+            if flatten:
+                out = out[1]
+            res = torch.autograd.grad((y * out).sum(), input, retain_graph=True)[0]
+        return res
 
     def _noise(self, shape_like, noiseless):
         return None if noiseless else torch.randn_like(shape_like)
@@ -70,7 +102,7 @@ class _SpectralOperator(LinearOperator):
         if y is not None:
             sf = getattr(self, "scale_factor", 1)
             from .diffpir_utils.utils_sisr import upsample
-            FBFy = FBC * torch.fft.fftn(upsample(y, sf) if sf > 1 else y, dim=(-2, -1))
+            FBFy = FBC * self.handle.fft2(upsample(y, sf) if sf > 1 else y)     # utils_sisr.py:91-95, on libkdip's FFT kernels
         return FB, FBC, F2B, FBFy
 
 
@@ -91,8 +123,8 @@ class _BlurOperator(_SpectralOperator):
 
     def forward(self, data, flatten=False, noiseless=False):
         # y = A x + sigma_s * randn_like(y): the noise add is fused into the inverse-FFT epilogue
-        y = self.handle.forward(data, None if noiseless else torch.randn_like(data, dtype=torch.float32))
-        self._set_measurement(y)
+        y = _apply_forward(self.handle, data, None if noiseless else torch.randn_like(data, dtype=torch.float32))
+        self._set_measurement(y.detach())
         if flatten:
             return y, y.reshape(y.shape[0], -1)
         return y
@@ -143,12 +175,12 @@ class SuperResolutionOperator(_SpectralOperator):
 
     def forward(self, data, flatten=False, noiseless=False):
         if noiseless:
-            y = self.handle.forward(data, None)
+            y = _apply_forward(self.handle, data, None)
         else:
             B = data.shape[0]
             noise = torch.randn(B, *self.out_shape[-3:], device=data.device, dtype=torch.float32)
-            y = self.handle.forward(data, noise)
-        self._set_measurement(y)
+            y = _apply_forward(self.handle, data, noise)
+        self._set_measurement(y.detach())
         if flatten:
             return y, y.reshape(y.shape[0], -1)
         return y
@@ -175,9 +207,11 @@ class InpaintingOperator(LinearOperator):
         self._idx = torch.nonzero(self.mask[0].flatten() > 0).flatten().to(torch.int32).contiguous()
 
     def forward(self, data: torch.Tensor, flatten=False, noiseless=False):
-        y = self.handle.forward(data, None if noiseless else torch.randn_like(data))
+        y = _apply_forward(self.handle, data, None if noiseless else torch.randn_like(data))
         if flatten:
-            return y, ops.gather(y, self._idx)
+            # the gather is an index op: torch's own indexing keeps it differentiable when a graph is being recorded
+            yf = y.flatten(1)[:, self._idx.long()] if y.requires_grad else ops.gather(y, self._idx)
+            return y, yf
         return y
 
     def transpose(self, data, flatten=False):

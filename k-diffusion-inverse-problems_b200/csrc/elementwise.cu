@@ -121,12 +121,15 @@ __global__ void pmv_vjp_seed_kernel(const float* __restrict__ x0, const float* _
   const size_t HW = (size_t)HW4;
   const float ce = -s.recipm1, cd = s.recip * s.c_in;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < 3 * HW; i += (size_t)gridDim.x * blockDim.x) {
-    float4 m = ld4(x0 + (size_t)b * 3 * HW * 4, i), g = ld4(v + (size_t)b * 3 * HW * 4, i), se, di;
-    // clamp backward: gradient passes where the clamp is inactive
-    g.x = (m.x > -1.f && m.x < 1.f) ? g.x : 0.f;
-    g.y = (m.y > -1.f && m.y < 1.f) ? g.y : 0.f;
-    g.z = (m.z > -1.f && m.z < 1.f) ? g.z : 0.f;
-    g.w = (m.w > -1.f && m.w < 1.f) ? g.w : 0.f;
+    float4 g = ld4(v + (size_t)b * 3 * HW * 4, i), se, di;
+    if (x0 != nullptr) {
+      // clamp backward: gradient passes where the clamp is inactive (x0 == NULL: the unclamped v2 denoiser, condition.py:291)
+      const float4 m = ld4(x0 + (size_t)b * 3 * HW * 4, i);
+      g.x = (m.x > -1.f && m.x < 1.f) ? g.x : 0.f;
+      g.y = (m.y > -1.f && m.y < 1.f) ? g.y : 0.f;
+      g.z = (m.z > -1.f && m.z < 1.f) ? g.z : 0.f;
+      g.w = (m.w > -1.f && m.w < 1.f) ? g.w : 0.f;
+    }
     se.x = ce * g.x; se.y = ce * g.y; se.z = ce * g.z; se.w = ce * g.w;
     di.x = cd * g.x; di.y = cd * g.y; di.z = cd * g.z; di.w = cd * g.w;
     st4(seed + (size_t)b * 6 * HW * 4, i, se);

@@ -65,6 +65,20 @@ __global__ void otf_full_kernel(const float2* __restrict__ otf, int S, float2* _
   }
 }
 
+// batched variant: [planes][S][S/2+1] half spectra -> [planes][S][S] full spectra (Hermitian completion)
+__global__ void spec_full_kernel(const float2* __restrict__ half, int S, float2* __restrict__ full, size_t total) {
+  const int Sh = S / 2 + 1;
+  GS_LOOP(i, total) {
+    const int kx = (int)(i % S), ky = (int)((i / S) % S);
+    const size_t p = i / ((size_t)S * S);
+    const float2* h = half + p * S * Sh;
+    float2 v;
+    if (kx <= S / 2) v = h[(size_t)ky * Sh + kx];
+    else { v = h[(size_t)((S - ky) % S) * Sh + (S - kx)]; v.y = -v.y; }
+    full[i] = v;
+  }
+}
+
 // ---- super-resolution glue (utils_sisr.py:44-61) ----------------------------------------------------------------------
 // r[p][i][j] = y[p][i][j] - full[p][sf*i][sf*j]
 __global__ void sr_residual_kernel(const float* __restrict__ y, const float* __restrict__ full, float* __restrict__ r, int s,
@@ -532,6 +546,47 @@ extern "C" int kdip_op_transpose(const kdip_op* op, const float* y, float* x, in
   upsample_zero_kernel<<<grid1d(n), OP_THREADS, 0, st>>>(y, w.full[0], op->s, op->sf, n);
   KDIP_LAUNCH_CHECK();
   return blur_apply(op, w, w.full[0], 1, x, B * 3, 1.f, nullptr, 0.f, nullptr, st);
+}
+
+// Adjoint of operator.forward(noiseless) - what torch.autograd gives the reference's LinearOperator.auto_transpose
+// (measurements.py:48-52) and its DPS branch (condition.py:144-146): conj-OTF blur, the Resizer's adjoint (NOT the FFT-model
+// transpose of measurements.py:113-118), or the mask.  g has y's shape; x [B,3,S,S].
+extern "C" int kdip_op_forward_adjoint(const kdip_op* op, const float* g, float* x, int B, void* ws, size_t ws_bytes, kdip_stream_t s) {
+  KDIP_REQUIRE(op && g && x && B > 0, KDIP_EINVAL, "op_forward_adjoint: bad argument");
+  cudaStream_t st = (cudaStream_t)s;
+  const size_t n = (size_t)B * 3 * op->S * op->S;
+  if (op->kind == KDIP_OP_INPAINTING) {
+    mask_mul_kernel<<<grid1d(n), OP_THREADS, 0, st>>>(g, op->mask, x, (size_t)3 * op->S * op->S, n);
+    KDIP_LAUNCH_CHECK();
+    return KDIP_OK;
+  }
+  OpWs w;
+  int rc = get_ws(op, B, ws, ws_bytes, &w);
+  if (rc) return rc;
+  if (is_blur(op)) return blur_apply(op, w, g, 1, x, B * 3, 1.f, nullptr, 0.f, nullptr, st);
+  return resizer_adjoint(op, w, g, x, B * 3, st);
+}
+
+// fft2 over the last two axes of x [B,3,S,S] as interleaved complex64 [B,3,S,S] (torch.fft.fftn(dim=(-2,-1)) of
+// utils_sisr.py:91-95, used for the FBFy member of operator.pre_calculated)
+extern "C" int kdip_op_fft2(const kdip_op* op, const float* x, float* out_full, int B, void* ws, size_t ws_bytes, kdip_stream_t s) {
+  KDIP_REQUIRE(op && x && out_full && B > 0 && op->otf, KDIP_EINVAL, "op_fft2: needs a spectral operator (blur / super_resolution)");
+  cudaStream_t st = (cudaStream_t)s;
+  OpWs w;
+  int rc = get_ws(op, B, ws, ws_bytes, &w);
+  if (rc) return rc;
+  const int planes = B * 3, S = op->S;
+  rc = launch_rows_r2c(x, w.specA, planes, S, st);
+  if (rc) return rc;
+  SpecOp so;
+  memset(&so, 0, sizeof(so));
+  so.mode = SPEC_FORWARD_ONLY; so.planes_per_image = 3;
+  rc = launch_cols(w.specA, w.specB, planes, S, so, st);
+  if (rc) return rc;
+  const size_t tot = (size_t)planes * S * S;
+  spec_full_kernel<<<grid1d(tot), OP_THREADS, 0, st>>>(w.specB, S, reinterpret_cast<float2*>(out_full), tot);
+  KDIP_LAUNCH_CHECK();
+  return KDIP_OK;
 }
 
 // r = y - A x0 in measurement space (blur: S x S, SR: s x s, inpainting: masked residual)

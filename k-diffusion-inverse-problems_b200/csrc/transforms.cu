@@ -7,6 +7,9 @@
 //        H and W as fp32 matrix products with the orthonormal DCT matrix, plus the 3-point DCT across channels.
 // Both accept an optional per-element multiplier applied to the FORWARD output (theta in the transform domain), which
 // fuses the `theta * ot(m)` product of condition/condition.py:182,338,374,427.
+#include <stdlib.h>
+#include <string.h>
+
 #include "ops.cuh"
 
 namespace kdip {
@@ -16,16 +19,28 @@ static constexpr float kInvSqrt2 = 0.70710678118654752440f;
 // sub-band placement of pywt.coeffs_to_array: detail on rows -> row offset s, detail on cols -> col offset s
 // ('da' = cH -> rows [s,2s), cols [0,s); 'ad' = cV -> rows [0,s), cols [s,2s); 'dd' -> both).  One table so the
 // layout can be flipped if a PyWavelets install ever disagrees (parity unpinned, see oracle/transforms_ref.py).
-__device__ __forceinline__ void band_offset(int band /*0 da, 1 ad, 2 dd*/, int s, int& r0, int& c0) {
+// `swap` = 1 selects the other candidate (KDIP_DWT_LAYOUT=diagram: the PyWavelets docstring diagram, 'da' top-right): the two
+// layouts differ only by exchanging the cH / cV blocks of every level.
+__device__ __forceinline__ void band_offset(int band /*0 da, 1 ad, 2 dd*/, int s, int swap, int& r0, int& c0) {
+  if (swap && band < 2) band ^= 1;
   r0 = (band == 0 || band == 2) ? s : 0;
   c0 = (band == 1 || band == 2) ? s : 0;
+}
+// KDIP_DWT_LAYOUT: "code" (default; pywt.coeffs_to_array's slicing rule) or "diagram"
+static int dwt_layout_swap() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("KDIP_DWT_LAYOUT");
+    v = (e != nullptr && strcmp(e, "diagram") == 0) ? 1 : 0;
+  }
+  return v;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Haar level-3 forward: grid = planes * S/8 CTAs, one 8-row strip each
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) dwt_fwd_kernel(const float* __restrict__ x, const float* __restrict__ mul,
-                                                      float* __restrict__ out, int S, int mul_planes) {
+                                                      float* __restrict__ out, int S, int mul_planes, int swap) {
   extern __shared__ float sm[];
   float* a0 = sm;                 // [8][S]
   float* a1 = a0 + 8 * S;         // [4][S/2]
@@ -56,7 +71,7 @@ __global__ void __launch_bounds__(256) dwt_fwd_kernel(const float* __restrict__ 
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
         int r0, c0;
-        band_offset(k, C, r0, c0);
+        band_offset(k, C, swap, r0, c0);
         const size_t o = (size_t)(r0 + row) * S + c0 + c;
         dstp[o] = mulp ? band[k] * mulp[o] : band[k];
       }
@@ -75,7 +90,7 @@ __global__ void __launch_bounds__(256) dwt_fwd_kernel(const float* __restrict__ 
 }
 
 // Haar level-3 inverse: one CTA rebuilds an 8-row strip
-__global__ void __launch_bounds__(256) dwt_inv_kernel(const float* __restrict__ cf, float* __restrict__ out, int S) {
+__global__ void __launch_bounds__(256) dwt_inv_kernel(const float* __restrict__ cf, float* __restrict__ out, int S, int swap) {
   extern __shared__ float sm[];
   float* a0 = sm;                 // [8][S]   (final)
   float* a1 = a0 + 8 * S;         // [4][S/2]
@@ -97,7 +112,7 @@ __global__ void __launch_bounds__(256) dwt_inv_kernel(const float* __restrict__ 
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
         int r0, c0;
-        band_offset(k, C, r0, c0);
+        band_offset(k, C, swap, r0, c0);
         band[k] = src[(size_t)(r0 + row) * S + c0 + c];
       }
       const float aa = cur[r * C + c], da = band[0], ad = band[1], dd = band[2];
@@ -122,8 +137,9 @@ __global__ void __launch_bounds__(256) dwt_inv_kernel(const float* __restrict__ 
 int launch_dwt(const float* x, const float* mul, int mul_planes, float* out, int planes, int S, int inverse, cudaStream_t s) {
   KDIP_REQUIRE(S % 8 == 0 && S >= 8 && S <= 1024, KDIP_ESHAPE, "dwt: S=%d must be a multiple of 8 (level-3 Haar)", S);
   const size_t smem = (size_t)(8 * S + 2 * S + S / 2 + S / 8 + 8) * sizeof(float);
-  if (!inverse) dwt_fwd_kernel<<<planes * (S / 8), 256, smem, s>>>(x, mul, out, S, mul_planes > 0 ? mul_planes : planes);
-  else dwt_inv_kernel<<<planes * (S / 8), 256, smem, s>>>(x, out, S);
+  const int swap = dwt_layout_swap();
+  if (!inverse) dwt_fwd_kernel<<<planes * (S / 8), 256, smem, s>>>(x, mul, out, S, mul_planes > 0 ? mul_planes : planes, swap);
+  else dwt_inv_kernel<<<planes * (S / 8), 256, smem, s>>>(x, out, S, swap);
   KDIP_LAUNCH_CHECK();
   return KDIP_OK;
 }

@@ -61,6 +61,7 @@ def _sigma_arg(x, value):
 
 
 def _prep(x):
+    """Every sampler of this module is CUDA-only (the updates are libkdip kernels); a CPU tensor raises."""
     if not x.is_cuda:
         raise RuntimeError("kdip samplers run on CUDA tensors only (B200, sm_100a); there is no CPU fallback")
     return x.detach().contiguous().float()
@@ -81,7 +82,7 @@ def sample_euler(model, x, sigmas, extra_args=None, callback=None, disable=None,
             x = ops.churn_(x.clone(), eps, s_noise, hs.s[i], sigma_hat)
         denoised = model(x, _sigma_arg(x, sigma_hat), **extra_args)
         if callback is not None:
-            callback({'x': x, 'i': i, 'sigma': sigmas[i], 'sigma_hat': torch.tensor(sigma_hat), 'denoised': denoised})
+            callback({'x': x, 'i': i, 'sigma': sigmas[i], 'sigma_hat': torch.tensor(sigma_hat, device=x.device), 'denoised': denoised})
         dt = np.float32(hs.s[i + 1] - sigma_hat)
         x = ops.euler_step(x, denoised, sigma_hat, dt)
     return x
@@ -101,7 +102,7 @@ def sample_heun(model, x, sigmas, extra_args=None, callback=None, disable=None, 
             x = ops.churn_(x.clone(), eps, s_noise, hs.s[i], sigma_hat)
         denoised = model(x, _sigma_arg(x, sigma_hat), **extra_args)
         if callback is not None:
-            callback({'x': x, 'i': i, 'sigma': sigmas[i], 'sigma_hat': torch.tensor(sigma_hat), 'denoised': denoised})
+            callback({'x': x, 'i': i, 'sigma': sigmas[i], 'sigma_hat': torch.tensor(sigma_hat, device=x.device), 'denoised': denoised})
         dt = np.float32(hs.s[i + 1] - sigma_hat)
         if hs.s[i + 1] == 0:
             x = ops.euler_step(x, denoised, sigma_hat, dt)                       # Euler method
@@ -201,7 +202,7 @@ def sample_dpm_2(model, x, sigmas, extra_args=None, callback=None, disable=None,
         if gamma > 0:
             x = ops.churn_(x.clone(), eps, s_noise, hs.s[i], sigma_hat)
         denoised = model(x, _sigma_arg(x, sigma_hat), **extra_args)
-        _report(callback, x, i, sigmas, torch.tensor(sigma_hat), denoised)
+        _report(callback, x, i, sigmas, torch.tensor(sigma_hat, device=x.device), denoised)
         if hs.s[i + 1] == 0:
             x = ops.euler_step(x, denoised, sigma_hat, _F(hs.s[i + 1] - sigma_hat))
         else:

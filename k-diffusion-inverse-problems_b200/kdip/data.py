@@ -21,6 +21,7 @@ class ImageBatchLoader:
         lo, hi = (0, len(dataset)) if accelerator is None else accelerator.shard(len(dataset))
         self.index = list(range(lo, hi))
         self._stage = None
+        self._copied = None     # CUDA event recorded after the last H2D copy out of the pinned staging buffer
 
     def __len__(self):
         n = len(self.index)
@@ -37,6 +38,8 @@ class ImageBatchLoader:
             first = np.array(self.ds.load(keys[0]))
             H, W = first.shape[:2]
             stage = self._staging(len(keys), H, W)
+            if self._copied is not None:
+                self._copied.synchronize()      # the previous batch's DMA still reads the staging buffer until this event
             stage[0].copy_(torch.from_numpy(first))
             for i, key in enumerate(keys[1:], 1):
                 im = np.array(self.ds.load(key))
@@ -44,4 +47,6 @@ class ImageBatchLoader:
                     raise ValueError(f"{self.ds.paths[key]}: {im.shape[:2]} differs from the batch's {(H, W)}")
                 stage[i].copy_(torch.from_numpy(im))
             dev = stage.to(self.device, non_blocking=True)
+            self._copied = torch.cuda.Event()
+            self._copied.record()
             yield ops.images_u8_to_f32(dev),

@@ -99,6 +99,24 @@ class OperatorHandle:
         check(lib.kdip_op_transpose(self._h, ptr(y), ptr(x), B, ws, nb, stream_ptr()))
         return x
 
+    def forward_adjoint(self, g):
+        """Adjoint of forward(noiseless) applied to g (y's shape) -> [B,3,S,S]."""
+        g = _f32(g)
+        B = g.shape[0]
+        x = torch.empty(B, 3, self.S, self.S, device=g.device, dtype=torch.float32)
+        ws, nb = self._workspace(B)
+        check(lib.kdip_op_forward_adjoint(self._h, ptr(g), ptr(x), B, ws, nb, stream_ptr()))
+        return x
+
+    def fft2(self, x):
+        """torch.fft.fftn(x, dim=(-2, -1)) for x [B,3,S,S] on libkdip's FFT kernels -> complex64 [B,3,S,S]."""
+        x = _f32(x)
+        B = x.shape[0]
+        out = torch.empty(B, 3, self.S, self.S, 2, device=x.device, dtype=torch.float32)
+        ws, nb = self._workspace(B)
+        check(lib.kdip_op_fft2(self._h, ptr(x), ptr(out), B, ws, nb, stream_ptr()))
+        return torch.view_as_complex(out)
+
     def otf(self):
         fb = torch.empty(self.S, self.S, 2, device=self.device, dtype=torch.float32)
         check(lib.kdip_op_otf(self._h, ptr(fb), stream_ptr()))
@@ -192,11 +210,22 @@ def pmv_epilogue(unet_out, x, sc, var_mode=0):
     return x0, var
 
 
-def pmv_vjp_seed(x0_mean, v, sc):
-    B, _, H, W = x0_mean.shape
+def v2_vjp_scalars(sigma_host, device):
+    """kdip_pmv_scalars for the unclamped v2 denoiser x0 = x - sigma*eps: seed = (-sigma v, 0), direct = v."""
+    B = len(sigma_host)
+    arr = (PmvScalars * B)()
+    for b in range(B):
+        arr[b].c_in, arr[b].recip, arr[b].recipm1 = 1.0, 1.0, float(np.float32(sigma_host[b]))
+    return torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(device)
+
+
+def pmv_vjp_seed(x0_mean, v, sc, like=None):
+    """x0_mean None: no clamp mask (v2)."""
+    B, _, H, W = (x0_mean if x0_mean is not None else like).shape
     seed = torch.empty(B, 6, H, W, device=v.device, dtype=torch.float32)
-    direct = torch.empty_like(x0_mean)
-    check(lib.kdip_pmv_vjp_seed(ptr(x0_mean), ptr(_f32(v)), ptr(sc), ptr(seed), ptr(direct), B, H * W, stream_ptr()))
+    direct = torch.empty(B, 3, H, W, device=v.device, dtype=torch.float32)
+    v = _f32(v)
+    check(lib.kdip_pmv_vjp_seed(ptr(x0_mean), ptr(v), ptr(sc), ptr(seed), ptr(direct), B, H * W, stream_ptr()))
     return seed, direct
 
 
@@ -204,7 +233,8 @@ def guidance_combine(x0_mean, g, direct, coef, c_in=None, out=None):
     B = x0_mean.shape[0]
     chw = x0_mean[0].numel()
     hat = torch.empty_like(x0_mean) if out is None else out
-    check(lib.kdip_guidance_combine(ptr(x0_mean), ptr(_f32(g)), ptr(direct), ptr(_f32(coef)), ptr(c_in), ptr(hat), B, chw,
+    g, coef = _f32(g), _f32(coef)          # bound to locals: a converted temporary must outlive the launch
+    check(lib.kdip_guidance_combine(ptr(x0_mean), ptr(g), ptr(direct), ptr(coef), ptr(c_in), ptr(hat), B, chw,
                                     stream_ptr()))
     return hat
 
@@ -212,8 +242,9 @@ def guidance_combine(x0_mean, g, direct, coef, c_in=None, out=None):
 def lincomb(x, y, a, c):
     """out = a[b]*x + c[b]*y (per-image device scalars), unclipped."""
     B = x.shape[0]
+    x, a = _f32(x), _f32(a)
     out = torch.empty_like(x)
-    check(lib.kdip_lincomb(ptr(_f32(x)), ptr(y), ptr(_f32(a)), ptr(c), ptr(out), B, x[0].numel(), stream_ptr()))
+    check(lib.kdip_lincomb(ptr(x), ptr(y), ptr(a), ptr(c), ptr(out), B, x[0].numel(), stream_ptr()))
     return out
 
 
@@ -231,20 +262,23 @@ def v2_epilogue(unet_out, cov_out, x, sigma_dev, want_var):
 # ---- sampler updates -------------------------------------------------------------------------------------------------
 
 def churn_(x, noise, s_noise, sigma, sigma_hat):
-    check(lib.kdip_churn(ptr(x), ptr(_f32(noise)), float(s_noise), float(sigma), float(sigma_hat), x.numel(), stream_ptr()))
+    noise = _f32(noise)
+    check(lib.kdip_churn(ptr(x), ptr(noise), float(s_noise), float(sigma), float(sigma_hat), x.numel(), stream_ptr()))
     return x
 
 
 def euler_step(x, denoised, sigma_hat, dt, want_d=False):
     x_out = torch.empty_like(x)
     d = torch.empty_like(x) if want_d else None
-    check(lib.kdip_euler_step(ptr(x), ptr(_f32(denoised)), float(sigma_hat), float(dt), ptr(x_out), ptr(d), x.numel(), stream_ptr()))
+    denoised = _f32(denoised)
+    check(lib.kdip_euler_step(ptr(x), ptr(denoised), float(sigma_hat), float(dt), ptr(x_out), ptr(d), x.numel(), stream_ptr()))
     return (x_out, d) if want_d else x_out
 
 
 def heun_step(x, d, x2, denoised2, sigma_next, dt):
     x_out = torch.empty_like(x)
-    check(lib.kdip_heun_step(ptr(x), ptr(d), ptr(x2), ptr(_f32(denoised2)), float(sigma_next), float(dt), ptr(x_out), x.numel(),
+    denoised2 = _f32(denoised2)
+    check(lib.kdip_heun_step(ptr(x), ptr(d), ptr(x2), ptr(denoised2), float(sigma_next), float(dt), ptr(x_out), x.numel(),
                              stream_ptr()))
     return x_out
 
@@ -253,22 +287,25 @@ def lincomb3(x, a, y=None, b=0.0, z=None, c=0.0, out=None):
     """a*x + b*y + c*z with host scalars (kdip_lincomb3); y / z optional."""
     x = _f32(x)
     out = torch.empty_like(x) if out is None else out
-    check(lib.kdip_lincomb3(ptr(x), ptr(_f32(y)) if y is not None else None, ptr(_f32(z)) if z is not None else None,
-                            float(a), float(b), float(c), ptr(out), x.numel(), stream_ptr()))
+    y = _f32(y) if y is not None else None
+    z = _f32(z) if z is not None else None
+    check(lib.kdip_lincomb3(ptr(x), ptr(y), ptr(z), float(a), float(b), float(c), ptr(out), x.numel(), stream_ptr()))
     return out
 
 
 def gather(src, idx):
     B, M = src.shape[0], idx.numel()
     dst = torch.empty(B, M, device=src.device, dtype=torch.float32)
-    check(lib.kdip_gather(ptr(_f32(src)), ptr(idx), ptr(dst), B, src[0].numel(), M, stream_ptr()))
+    src = _f32(src)
+    check(lib.kdip_gather(ptr(src), ptr(idx), ptr(dst), B, src[0].numel(), M, stream_ptr()))
     return dst
 
 
 def scatter(src, idx, shape):
     B = src.shape[0]
     dst = torch.empty(B, *shape, device=src.device, dtype=torch.float32)
-    check(lib.kdip_scatter(ptr(_f32(src)), ptr(idx), ptr(dst), B, dst[0].numel(), idx.numel(), stream_ptr()))
+    src = _f32(src)
+    check(lib.kdip_scatter(ptr(src), ptr(idx), ptr(dst), B, dst[0].numel(), idx.numel(), stream_ptr()))
     return dst
 
 
@@ -307,7 +344,8 @@ def denoise_sqerr(unet_out, x_noised, x0, sigma_dev, want_hat=False):
     B, _, H, W = x0.shape
     out = torch.empty(B, device=x0.device, dtype=torch.float64)
     hat = torch.empty_like(x0) if want_hat else None
-    check(lib.kdip_denoise_sqerr(ptr(unet_out), ptr(x_noised), ptr(x0), ptr(_f32(sigma_dev)), ptr(out), ptr(hat), B, H * W, stream_ptr()))
+    sigma_dev = _f32(sigma_dev)
+    check(lib.kdip_denoise_sqerr(ptr(unet_out), ptr(x_noised), ptr(x0), ptr(sigma_dev), ptr(out), ptr(hat), B, H * W, stream_ptr()))
     return (out, hat) if want_hat else out
 
 

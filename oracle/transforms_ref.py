@@ -13,13 +13,19 @@ is a restatement of its published conventions — PARITY UNPINNED for the packed
   'd' on an axis -> slice [s:2s] on that axis, 'a' -> [0:s]   (so cH='da' -> rows [s:2s], cols [0:s]).
 The layout is one table (`DWT_SLOT`) so it can be flipped once checked against a pywt install.
 """
+import os
+
 import numpy as np
 import scipy.fft
 import torch
 
 LEVEL = 3
-# block name -> (row_is_detail, col_is_detail)
-DWT_SLOT = {"da": (1, 0), "ad": (0, 1), "dd": (1, 1)}
+# block name -> (row_is_detail, col_is_detail).  "code" = the slicing rule of pywt.coeffs_to_array as restated above;
+# "diagram" = the placement drawn in the PyWavelets docstring ('da' top-right).  Same switch as csrc/transforms.cu
+# (KDIP_DWT_LAYOUT); tests/golden/make_golden_pywt.py settles it on a machine that has PyWavelets.
+DWT_LAYOUTS = {"code": {"da": (1, 0), "ad": (0, 1), "dd": (1, 1)},
+               "diagram": {"da": (0, 1), "ad": (1, 0), "dd": (1, 1)}}
+DWT_SLOT = DWT_LAYOUTS[os.environ.get("KDIP_DWT_LAYOUT", "code")]
 
 
 def dct_forward(x):
@@ -50,9 +56,10 @@ def _haar_merge(lo, hi, axis):
     return np.moveaxis(out, -1, axis)
 
 
-def dwt_forward(x):
+def dwt_forward(x, slot=None):
     """condition/utils.py:116-123: level-3 Haar, packed like pywt.coeffs_to_array. float32 in/out
     (pywt computes float32 input in float32)."""
+    DWT_SLOT = slot or globals()["DWT_SLOT"]
     a = x.detach().numpy().astype(np.float32)
     out = np.empty_like(a)
     cur = a
@@ -69,8 +76,9 @@ def dwt_forward(x):
     return torch.tensor(out)
 
 
-def dwt_inverse(x):
+def dwt_inverse(x, slot=None):
     """condition/utils.py:125-132: array_to_coeffs + waverec2."""
+    DWT_SLOT = slot or globals()["DWT_SLOT"]
     a = x.detach().numpy().astype(np.float32)
     s = a.shape[-1] >> LEVEL
     cur = a[..., :s, :s]
