@@ -266,6 +266,8 @@ int kdip_pack_conv_weight(const float* w_oihw, int Cout, int Cin, int taps, int 
  * (guided_diffusion/script_util.py:130-184) with condition/diffpir_utils/utils_model.py:353-387 defaults:
  * resblock_updown, use_scale_shift_norm, learn_sigma (6 output channels), legacy attention order, head width 64.
  * ------------------------------------------------------------------------------------------------------------ */
+#define KDIP_PRECISION_BF16 0
+#define KDIP_PRECISION_FP32 1
 typedef struct {
   int image_size;         /* 256 (FFHQ / ImageNet) or 64 (test geometry)                      */
   int in_channels;        /* 3                                                                */
@@ -277,6 +279,10 @@ typedef struct {
   float channel_mult[8];  /* script_util.py:148-160                                           */
   int n_att;
   int attention_ds[8];    /* downsample rates with attention, script_util.py:162-164          */
+  int precision;          /* KDIP_PRECISION_BF16 (0): bf16 tcgen05 operands, fp32 accumulation - the fast path;
+                             KDIP_PRECISION_FP32 (1): fp32 FMA on fp32 operands throughout, the reference's own arithmetic
+                             (use_fp16=False, condition/diffpir_utils/utils_model.py:364) - CUDA cores, ~40x slower, for
+                             tight-tolerance parity against the reference                  */
 } kdip_unet_arch;
 
 typedef struct kdip_unet kdip_unet;

@@ -22,8 +22,21 @@
 #include <vector>
 
 #include "unet_kernels.cuh"
+#include "unet_plan.h"
 
 namespace kdip {
+
+// fp32 reference-precision engine (unet_fp32.cu), selected by kdip_unet_arch.precision
+struct Fp32Engine;
+int fp32_create(const kdip_unet_arch* arch, const std::map<std::string, std::pair<const float*, int64_t>>& src, Fp32Engine** out);
+void fp32_destroy(Fp32Engine* e);
+bool fp32_has_cov(const Fp32Engine* e);
+int fp32_workspace_bytes(Fp32Engine* e, int N, size_t* bytes);
+int fp32_prepare(Fp32Engine* e, int N, void* ws, size_t ws_bytes);
+int fp32_forward(Fp32Engine* e, const float* x, const float* x_scale, const float* t, int N, float* out, float* cov_out, void* ws,
+                 size_t ws_bytes, cudaStream_t s);
+int fp32_vjp(Fp32Engine* e, const float* seed, int N, float* grad_x, void* ws, size_t ws_bytes, cudaStream_t s);
+int fp32_feature(Fp32Engine* e, int N, float* feat, cudaStream_t s);
 
 struct ConvPlan;  // conv_gemm.cu
 int conv_plan_build(const kdip_conv_desc* d, ConvPlan* plan);
@@ -34,17 +47,6 @@ void conv_plan_free(ConvPlan* p);
 
 int pack_weight_ex(const float* w, int Cout, int Cin_total, int ci_off, int Cin_sub, int taps, int rows_pad, int cols_pad,
                    int flip, void* dst, cudaStream_t s);
-
-struct BlockDesc {
-  std::string prefix;
-  int kind;      // 0 conv_in, 1 res, 2 attn
-  int cin, cout;
-  int updown;    // 0 none, 1 down, 2 up
-  int stage;     // 0 in, 1 mid, 2 out
-  int block;     // index of the enclosing TimestepEmbedSequential
-  int skip_ch;   // channels popped from the skip stack (out-stage res blocks that start a block)
-  bool first_of_block, last_of_block;
-};
 
 struct DevBuf {
   void* p = nullptr;
@@ -91,6 +93,7 @@ static double conv_flops(const kdip_conv_desc& d) {
 using namespace kdip;
 
 struct kdip_unet {
+  kdip::Fp32Engine* f32 = nullptr;               // set instead of everything below when arch.precision == KDIP_PRECISION_FP32
   kdip_unet_arch arch;
   std::vector<BlockDesc> plan;
   std::map<std::string, const float*> fp32;   // small fp32 params resident on device (owned, see owned[])
@@ -144,7 +147,7 @@ static bool in_list(const int* a, int n, int v) {
   return false;
 }
 
-static void build_block_plan(const kdip_unet_arch& a, std::vector<BlockDesc>& plan) {
+void build_block_plan(const kdip_unet_arch& a, std::vector<BlockDesc>& plan) {
   plan.clear();
   const int mc = a.model_channels;
   auto push = [&](const std::string& prefix, int kind, int cin, int cout, int updown, int stage, int block, int skip_ch) {
@@ -216,6 +219,7 @@ static int dev_alloc(kdip_unet* u, size_t bytes, void** out) {
 
 extern "C" void kdip_unet_destroy(kdip_unet* u) {
   if (!u) return;
+  if (u->f32) fp32_destroy(u->f32);
   for (void* p : u->owned) cudaFree(p);
   for (ConvPlan* c : u->conv_plans) conv_plan_free(c);
   delete u;
@@ -228,6 +232,8 @@ extern "C" int kdip_unet_create(const kdip_unet_arch* arch, int n_tensors, const
   KDIP_REQUIRE(arch->num_head_channels == 64, KDIP_ESHAPE, "unet_create: num_head_channels must be 64 (got %d)", arch->num_head_channels);
   KDIP_REQUIRE(arch->in_channels == 3 && arch->out_channels == 6, KDIP_ESHAPE, "unet_create: in/out channels must be 3/6");
   KDIP_REQUIRE(arch->model_channels % 64 == 0, KDIP_ESHAPE, "unet_create: model_channels must be a multiple of 64");
+  KDIP_REQUIRE(arch->precision == KDIP_PRECISION_BF16 || arch->precision == KDIP_PRECISION_FP32, KDIP_EINVAL,
+               "unet_create: precision must be KDIP_PRECISION_BF16 or KDIP_PRECISION_FP32 (got %d)", arch->precision);
   int rc = kdip_device_check(nullptr);
   if (rc != KDIP_OK) return rc;
   kdip_unet* u = new kdip_unet();
@@ -235,6 +241,13 @@ extern "C" int kdip_unet_create(const kdip_unet_arch* arch, int n_tensors, const
   build_block_plan(*arch, u->plan);
   std::map<std::string, std::pair<const float*, int64_t>> src;
   for (int i = 0; i < n_tensors; ++i) src[names[i]] = std::make_pair(ptrs[i], numels[i]);
+  if (arch->precision == KDIP_PRECISION_FP32) {
+    rc = fp32_create(arch, src, &u->f32);
+    if (rc != KDIP_OK) { delete u; return rc; }
+    u->has_cov = fp32_has_cov(u->f32);
+    *out = u;
+    return KDIP_OK;
+  }
   cudaStream_t s = 0;
   auto fail = [&](int code) { kdip_unet_destroy(u); return code; };
 
@@ -927,13 +940,16 @@ extern "C" int kdip_unet_schema_entry(const kdip_unet_arch* arch, int index, cha
 
 // pre-head feature of the last forward as fp32 NCHW [N, C0, S, S] (UNetModel.forward(return_feature=True), unet.py:665-666)
 extern "C" int kdip_unet_feature(kdip_unet* u, int N, float* feat, kdip_stream_t s) {
-  KDIP_REQUIRE(u && feat && u->planned_N == N && u->hlast_ptr, KDIP_EINVAL, "unet_feature: must follow kdip_unet_forward with the same N");
+  KDIP_REQUIRE(u && feat, KDIP_EINVAL, "unet_feature: null argument");
+  if (u->f32) return fp32_feature(u->f32, N, feat, (cudaStream_t)s);
+  KDIP_REQUIRE(u->planned_N == N && u->hlast_ptr, KDIP_EINVAL, "unet_feature: must follow kdip_unet_forward with the same N");
   const int S = u->arch.image_size, c0 = (int)(u->arch.channel_mult[0] * u->arch.model_channels);
   return kdip_nhwc_bf16_to_nchw_f32(u->hlast_ptr, N, c0, S, S, feat, s);
 }
 
 extern "C" int kdip_unet_workspace_bytes(kdip_unet* u, int N, size_t* bytes) {
   KDIP_REQUIRE(u && bytes && N > 0, KDIP_EINVAL, "unet_workspace_bytes: bad argument");
+  if (u->f32) return fp32_workspace_bytes(u->f32, N, bytes);
   return build_launch_plan(u, N, nullptr, 0, bytes);
 }
 
@@ -948,6 +964,7 @@ static int ensure_plan(kdip_unet* u, int N, void* ws, size_t ws_bytes) {
 
 extern "C" int kdip_unet_prepare(kdip_unet* u, int N, void* workspace, size_t ws_bytes) {
   KDIP_REQUIRE(u && N > 0, KDIP_EINVAL, "unet_prepare: bad argument");
+  if (u->f32) return fp32_prepare(u->f32, N, workspace, ws_bytes);
   return ensure_plan(u, N, workspace, ws_bytes);
 }
 
@@ -1005,6 +1022,7 @@ extern "C" int kdip_unet_forward(kdip_unet* u, const float* x, const float* x_sc
                                  float* cov_out, void* workspace, size_t ws_bytes, kdip_stream_t stream) {
   KDIP_REQUIRE(u && x && t && out && N > 0, KDIP_EINVAL, "unet_forward: bad argument");
   KDIP_REQUIRE(cov_out == nullptr || u->has_cov, KDIP_EINVAL, "unet_forward: cov_out requested but no out_cov weights were given");
+  if (u->f32) return fp32_forward(u->f32, x, x_scale, t, N, out, cov_out, workspace, ws_bytes, (cudaStream_t)stream);
   int rc = ensure_plan(u, N, workspace, ws_bytes);
   if (rc != KDIP_OK) return rc;
   cudaStream_t s = (cudaStream_t)stream;
@@ -1041,6 +1059,7 @@ static int vjp_tail(kdip_unet* u, int N, float* grad_x, cudaStream_t s, double* 
 extern "C" int kdip_unet_vjp(kdip_unet* u, const float* seed, int N, float* grad_x, void* workspace, size_t ws_bytes,
                              kdip_stream_t stream) {
   KDIP_REQUIRE(u && seed && grad_x && N > 0, KDIP_EINVAL, "unet_vjp: bad argument");
+  if (u->f32) return fp32_vjp(u->f32, seed, N, grad_x, workspace, ws_bytes, (cudaStream_t)stream);
   KDIP_REQUIRE(u->planned_N == N && u->planned_ws == workspace && u->planned_bytes == ws_bytes, KDIP_EINVAL,
                "unet_vjp: must follow kdip_unet_forward with the same N and workspace (saved activations live there)");
   cudaStream_t s = (cudaStream_t)stream;
@@ -1057,6 +1076,7 @@ extern "C" int kdip_unet_profile(kdip_unet* u, const float* x, const float* x_sc
                                  float* out, float* grad_x, void* workspace, size_t ws_bytes, kdip_stream_t stream,
                                  kdip_unet_profile_t* prof) {
   KDIP_REQUIRE(u && x && t && out && seed && grad_x && prof && N > 0, KDIP_EINVAL, "unet_profile: bad argument");
+  KDIP_REQUIRE(u->f32 == nullptr, KDIP_EINVAL, "unet_profile: only the bf16 tcgen05 engine is instrumented");
   int rc = ensure_plan(u, N, workspace, ws_bytes);
   if (rc != KDIP_OK) return rc;
   cudaStream_t s = (cudaStream_t)stream;

@@ -109,12 +109,22 @@ class UNetModel(nn.Module):
         self._engine = None
         self._engine_key = None
         self.out_cov = None   # set by OpenAIDenoiserV2 to fuse its covariance head
+        # engine arithmetic: "bf16" (tcgen05 fast path) or "fp32" (the reference's use_fp16=False arithmetic, CUDA cores);
+        # assign model.precision = "fp32" (or export KDIP_PRECISION=fp32) before the first forward
+        import os
+        self.precision = os.environ.get("KDIP_PRECISION", "bf16")
 
     # ---- engine management ---------------------------------------------------------------------------------------
     def _weights_key(self):
         ps = list(self.parameters())
         return (ps[0].device, tuple(p._version for p in ps), tuple(p.data_ptr() for p in ps[:4]),
-                None if self.out_cov is None else tuple(p._version for p in self.out_cov))
+                None if self.out_cov is None else tuple(p._version for p in self.out_cov), self.precision)
+
+    def invalidate(self):
+        """Drop the packed engine: call after editing weights in place through ``p.data`` (EMA-style updates do not bump
+        ``Parameter._version``, which is what the engine cache keys on)."""
+        self._engine = None
+        self._engine_key = None
 
     def engine(self):
         """(Re)pack the weights into the device engine when they changed (load_state_dict / .to())."""
@@ -129,7 +139,7 @@ class UNetModel(nn.Module):
                                       num_res_blocks=self.num_res_blocks,
                                       attention_resolutions=",".join(str(self.image_size // d) for d in self.attention_resolutions),
                                       num_head_channels=self.num_head_channels, channel_mult=self.channel_mult,
-                                      out_cov=self.out_cov, device=dev)
+                                      out_cov=self.out_cov, device=dev, precision=self.precision)
             self._engine_key = key
         return self._engine
 

@@ -106,7 +106,7 @@ class UNetArch(ctypes.Structure):
     _fields_ = [("image_size", ctypes.c_int), ("in_channels", ctypes.c_int), ("model_channels", ctypes.c_int),
                 ("out_channels", ctypes.c_int), ("num_res_blocks", ctypes.c_int), ("num_head_channels", ctypes.c_int),
                 ("n_mult", ctypes.c_int), ("channel_mult", ctypes.c_float * 8), ("n_att", ctypes.c_int),
-                ("attention_ds", ctypes.c_int * 8)]
+                ("attention_ds", ctypes.c_int * 8), ("precision", ctypes.c_int)]
 
 
 def stream_ptr():

@@ -19,7 +19,9 @@ class UNetEngine:
     """Owns the packed weights (inside libkdip) and the activation workspace (a torch uint8 tensor)."""
 
     def __init__(self, state_dict, image_size=256, num_channels=128, num_res_blocks=1, attention_resolutions="16",
-                 num_head_channels=64, channel_mult=None, out_cov=None, device="cuda"):
+                 num_head_channels=64, channel_mult=None, out_cov=None, device="cuda", precision="bf16"):
+        """precision: "bf16" = bf16 tcgen05 operands with fp32 accumulation (the fast path); "fp32" = the reference's own fp32
+        arithmetic on the CUDA cores (csrc/unet_fp32.cu), for tight-tolerance parity."""
         if not torch.cuda.is_available():
             raise RuntimeError("kdip.UNetEngine needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.device = torch.device(device)
@@ -34,6 +36,10 @@ class UNetEngine:
         arch.n_att = len(att)
         for i, d in enumerate(att):
             arch.attention_ds[i] = int(d)
+        if precision not in ("bf16", "fp32"):
+            raise ValueError(f"UNetEngine precision must be 'bf16' or 'fp32' (got {precision!r})")
+        self.precision = precision
+        arch.precision = 1 if precision == "fp32" else 0
         self.arch = arch
         self.image_size = image_size
         tensors = {k: v.detach().to(self.device, torch.float32).contiguous() for k, v in state_dict.items()}

@@ -1,14 +1,18 @@
 """Guided model evaluations and sampler trajectories through the public API (condition.ConditionOpenAIDenoiser,
-k_diffusion.sampling) on the GPU vs the reference's golden vectors.
+k_diffusion.sampling) on the GPU vs the reference's golden vectors, in BOTH engine precisions.
 
-Stated tolerance.  The UNet runs bf16 tensor-core GEMMs with fp32 accumulation (forward AND input-VJP, relative L2 error
-1e-2 / 1.7e-2 against the fp32 reference, tests/test_unet_gpu.py); everything else is fp32.  hat_x0 = clip(x0 + sigma^2 J^T v)
-is NOT a well-conditioned function of the network at large sigma with the synthetic weights: sigma^2 |J^T v| reaches ~90 and
-the clamp inside the differentiated graph (gaussian_diffusion.py:296-297) switches a pixel's direct term on or off when x0
-crosses +-1.  The reference algorithm itself, evaluated in exact fp32 but with its WEIGHTS rounded to bf16 (a 2^-9 relative
-perturbation), moves hat_x0 by 0.25-0.28 relative L2 at sigma = 10 and its 4-6 step trajectories by 0.57-0.75.  So each
-case is held to:  relative L2 error <= max(floor, 2 x that bf16-weight sensitivity of the reference) and fraction of pixels
-off by > 6e-2 <= max(3 %, 3 x the reference's), computed in the test by the CPU oracle; floor = 6e-2 max / 3e-2 relative L2 per evaluation.  Well-conditioned cases (sigma <= 1.5) pass the floor alone.
+Stated tolerances - all fixed numbers, nothing is calibrated inside a test:
+  precision="fp32" (csrc/unet_fp32.cu: the reference's own fp32 arithmetic): relative L2 <= 2e-3 for EVERY guided evaluation
+      (TOL_FP32; measured values are ~1e-5 and are written to profiles/parity_r2.json by the parity_log fixture).
+  precision="bf16" (the tcgen05 fast path: bf16 operands, fp32 accumulation; UNet forward / VJP 1e-2 / 1.7e-2 off the fp32
+      reference, tests/test_unet_gpu.py): sigma <= 1.5: max error < 6e-2 and relative L2 < 3e-2 (BF16_FLOOR).  At sigma >= 3
+      hat_x0 = clip(x0 + sigma^2 J^T v) amplifies a relative perturbation of the network 20-80x with the synthetic weights
+      (tests/tools/sensitivity.py, run on the CPU oracle: 6e-8 -> 5e-6..2e-5, 4e-6 -> 1e-4..3.5e-4), so bf16's ~1e-2 lands at
+      0.2-0.5: those cases only assert the fixed sanity bound BF16_ILL_L2 and are NOT a parity claim - the parity claim for
+      them is the fp32 engine running the very same host path, guidance kernels and operators.
+Sampler trajectories with the UNet in the loop are chaotic with these weights (the reference itself, with its weights perturbed
+by 6e-8, moves the 6-step Euler run by 4e-2): every step is checked on its own from the reference's state (golden_traj_small),
+the free-running drift is recorded and held to the fixed per-run bounds TRAJ_FREE_*.
 The sampler arithmetic itself is checked to fp32 accuracy with an analytic denoiser (test_sampler_exact_with_analytic_model)."""
 import numpy as np
 import pytest
@@ -19,14 +23,32 @@ from test_operators_gpu import cpu_noise, make_op, make_ref, ref_noise
 
 pytestmark = pytest.mark.gpu
 
+PRECISIONS = ["fp32", "bf16"]
+TOL_FP32 = 2e-3                 # relative L2, every guided evaluation, fp32 engine
+BF16_FLOOR = (6e-2, 3e-2)       # (max, relative L2), bf16 engine, sigma <= 1.5
+BF16_ILL_L2 = 0.6               # bf16 engine, sigma >= 3: sanity bound only (module docstring)
+# free-running final sample of each tiny trajectory, relative L2: (fp32 bound, bf16 bound)
+TRAJ_FREE = {"inpaint_pgdm_euler6": (0.15, 1.5), "gauss_pgdm_heun4": (2e-3, 1.5), "gauss_pgdm_heun4_churn": (2e-3, 1.5)}
+TRAJ_STEP_BF16 = 5e-2           # one sampler step from the reference's state, bf16 engine (x_{i+1} is dominated by x_i)
+
+
+def check_eval(name, precision, sigma, e_max, e_l2, parity_log, **more):
+    parity_log(f"{name}[{precision}]", e_max=e_max, e_l2=e_l2, sigma=sigma, **more)
+    print(f"{name} [{precision}]: max {e_max:.3e} l2 {e_l2:.3e}")
+    if precision == "fp32":
+        assert e_l2 <= TOL_FP32, (name, e_max, e_l2)
+    elif sigma <= 1.5:
+        assert e_max < BF16_FLOOR[0] and e_l2 < BF16_FLOOR[1], (name, e_max, e_l2)
+    else:
+        assert e_l2 <= BF16_ILL_L2, (name, e_max, e_l2)
+
 
 def errs(got, ref):
     got, ref = torch.as_tensor(got).float().cpu(), torch.as_tensor(ref).float().cpu()
     return (got - ref).abs().max().item(), ((got - ref).norm() / ref.norm().clamp_min(1e-12)).item()
 
 
-@pytest.fixture(scope="module")
-def tiny_model():
+def _tiny(precision):
     from oracle import unet_ref
     from guided_diffusion.script_util import create_gaussian_diffusion
     from guided_diffusion.unet import UNetModel
@@ -36,7 +58,24 @@ def tiny_model():
                       attention_resolutions=cfg.attention_ds(), channel_mult=cfg.resolved_channel_mult(), num_head_channels=64,
                       use_scale_shift_norm=True, resblock_updown=True)
     model.load_state_dict(sd, strict=True)
+    model.precision = precision
     return model.eval().cuda(), create_gaussian_diffusion(learn_sigma=True)
+
+
+@pytest.fixture(scope="module")
+def tiny_models():
+    cache = {}
+
+    def get(precision):
+        if precision not in cache:
+            cache[precision] = _tiny(precision)
+        return cache[precision]
+    return get
+
+
+@pytest.fixture(scope="module")
+def tiny_model(tiny_models):
+    return tiny_models("bf16")
 
 
 def measurement(op, name, size=64, batch=1):
@@ -45,19 +84,6 @@ def measurement(op, name, size=64, batch=1):
     if batch > 1:
         y = y.expand(batch, -1, -1, -1).contiguous()
     return y, y.reshape(y.shape[0], -1)
-
-
-_BF16 = {}
-
-
-def bf16_weight_oracle():
-    """The CPU oracle with its weights rounded to bf16 (all arithmetic fp32): the reference's own sensitivity probe."""
-    from oracle import unet_ref
-    if not _BF16:
-        cfg = unet_ref.tiny_config()
-        sd = unet_ref.init_state_dict(cfg, seed=0)
-        _BF16.update(cfg=cfg, sd={k: v.to(torch.bfloat16).float() for k, v in sd.items()})
-    return _BF16["cfg"], _BF16["sd"]
 
 
 def oracle_measurement(name):
@@ -72,10 +98,11 @@ def recon_mse():
     return {"sigmas": s[:-1].clone(), "mse_list": 0.5 * s[:-1] ** 2 / (1 + s[:-1] ** 2)}
 
 
+@pytest.mark.parametrize("precision", PRECISIONS)
 @pytest.mark.parametrize("combo", I.GUIDANCE_COMBOS, ids=lambda c: f"{c[0]}-{c[1]}-{c[2]}-{c[3]}")
-def test_guided_eval(combo, tiny_model, golden_small):
+def test_guided_eval(combo, precision, tiny_models, golden_small, parity_log):
     from condition.condition import ConditionOpenAIDenoiser
-    model, diffusion = tiny_model
+    model, diffusion = tiny_models(precision)
     opname, guidance, cov, sigma, extra = combo
     op = make_op(opname, 64)
     cm = ConditionOpenAIDenoiser(inner_model=model, diffusion=diffusion, x0_cov_type=cov, recon_mse=recon_mse(), operator=op,
@@ -83,40 +110,28 @@ def test_guided_eval(combo, tiny_model, golden_small):
                                  **extra).eval()
     xt = I.xt(64, sigma, seed=21).cuda()
     hat = cm(xt, torch.tensor([sigma]).cuda())
-    e_max, e_l2 = errs(hat, golden_small[f"guid.{opname}.{guidance}.{cov}.{sigma}"])
-    print(f"guided eval {opname}/{guidance}/{cov}/{sigma}: max {e_max:.3e} l2 {e_l2:.3e}")
     assert torch.isfinite(hat).all()
-    gold = golden_small[f"guid.{opname}.{guidance}.{cov}.{sigma}"]
-    well = e_max < 6e-2 and e_l2 < 3e-2
-    s_l2 = 0.0
-    if not well:
-        # ill-conditioned case: measure the reference's own sensitivity to bf16 weight rounding (module docstring)
-        from oracle import guidance_ref
-        cfg, sd_b = bf16_weight_oracle()
-        ref_op, meas = oracle_measurement(opname)
-        probe = guidance_ref.ConditionDenoiserRef(sd_b, cfg, ref_op, meas, guidance, cov, recon_mse=recon_mse(), mle_sigma_thres=0.2, **extra)
-        s_max, s_l2 = errs(probe(I.xt(64, sigma, seed=21), torch.tensor([sigma])), gold)
-        frac = ((hat.cpu() - torch.as_tensor(gold)).abs() > 6e-2).float().mean().item()
-        s_frac = ((probe(I.xt(64, sigma, seed=21), torch.tensor([sigma])) - torch.as_tensor(gold)).abs() > 6e-2).float().mean().item()
-        print(f"   bf16-weight sensitivity of the reference: max {s_max:.3e} l2 {s_l2:.3e} frac>6e-2 {s_frac:.3f} (ours {frac:.3f})")
-        assert e_l2 <= max(3e-2, 2 * s_l2) and frac <= max(0.03, 3 * s_frac)
+    gold = torch.as_tensor(golden_small[f"guid.{opname}.{guidance}.{cov}.{sigma}"])
+    e_max, e_l2 = errs(hat, gold)
+    frac = ((hat.cpu() - gold).abs() > 6e-2).float().mean().item()
+    check_eval(f"guided.{opname}.{guidance}.{cov}.{sigma}", precision, sigma, e_max, e_l2, parity_log, frac_gt_6e2=frac)
     # batch of 3 identical problems == the single problem (images are independent units)
     cm3 = ConditionOpenAIDenoiser(inner_model=model, diffusion=diffusion, x0_cov_type=cov, recon_mse=recon_mse(), operator=op,
                                   measurement=measurement(op, opname, batch=3), guidance=guidance, device="cuda",
                                   mle_sigma_thres=0.2, **extra).eval()
     hat3 = cm3(xt.expand(3, -1, -1, -1).contiguous(), torch.full((3,), sigma).cuda())
     b_max, b_l2 = errs(hat3[2:3], hat)
-    print(f"   batch-of-3 vs single: max {b_max:.3e} l2 {b_l2:.3e}")
-    # only the accumulation order of the GroupNorm statistics differs between the two runs (atomics): bf16-level noise,
-    # amplified like any other perturbation in the ill-conditioned cases
-    assert b_l2 <= (1e-2 if well else 2 * s_l2)
+    # bf16 engine: the accumulation order of the fused GroupNorm statistics differs between the two runs (atomics), i.e. bf16-level
+    # noise that is amplified like any other perturbation in the ill-conditioned cases; fp32 engine: deterministic reductions
+    check_eval(f"guided.{opname}.{guidance}.{cov}.{sigma}.batch3_vs_single", precision, sigma, b_max, b_l2, parity_log)
 
 
+@pytest.mark.parametrize("precision", PRECISIONS)
 @pytest.mark.parametrize("run", I.SAMPLER_RUNS, ids=lambda r: r[0])
-def test_sampler_trajectory(run, tiny_model, golden_small):
+def test_sampler_trajectory(run, precision, tiny_models, golden_small, golden_traj_small, parity_log):
     from condition.condition import ConditionOpenAIDenoiser
     import k_diffusion as K
-    model, diffusion = tiny_model
+    model, diffusion = tiny_models(precision)
     tag, opname, guidance, cov, sampler, n, churn = run
     op = make_op(opname, 64)
     cm = ConditionOpenAIDenoiser(inner_model=model, diffusion=diffusion, x0_cov_type=cov, recon_mse=None, operator=op,
@@ -128,21 +143,20 @@ def test_sampler_trajectory(run, tiny_model, golden_small):
     noises = [torch.randn(1, 3, 64, 64) for _ in range(n)]
     kw = dict(s_churn=80, s_tmin=0.05, s_tmax=50, s_noise=1.003) if churn else {}
     out = fn(cm, I.xT(64, seed=3).cuda(), sig, disable=True, noise_sampler=lambda i, x: noises[i].to(x.device), **kw)
-    gold = golden_small[f"traj.{tag}"]
-    e_max, e_l2 = errs(out, gold)
-    print(f"trajectory {tag}: max {e_max:.3e} l2 {e_l2:.3e}")
     assert torch.isfinite(out).all()
-    if e_l2 >= 5e-2:
-        # chaotic with synthetic weights (module docstring): hold to 1.5x the reference's bf16-weight sensitivity
-        from oracle import guidance_ref, sampler_ref
-        cfg, sd_b = bf16_weight_oracle()
-        ref_op, meas = oracle_measurement(opname)
-        probe = guidance_ref.ConditionDenoiserRef(sd_b, cfg, ref_op, meas, guidance, cov)
-        rfn = sampler_ref.sample_euler if sampler == "euler" else sampler_ref.sample_heun
-        ref_out = rfn(probe, I.xT(64, seed=3), sampler_ref.get_sigmas_karras(n, 0.01, 80), noise_fn=lambda i, x: noises[i], **kw)
-        s_l2 = errs(ref_out, gold)[1]
-        print(f"   bf16-weight sensitivity of the reference trajectory: l2 {s_l2:.3e}")
-        assert e_l2 <= 1.5 * s_l2
+    e_max, e_l2 = errs(out, golden_small[f"traj.{tag}"])
+    steps = []
+    if not churn:
+        # every step on its own, started from the reference's state (a two-entry schedule slice is exactly step i of the loop)
+        for i in range(n):
+            xi = torch.as_tensor(golden_traj_small[f"traj.{tag}.x{i}"]).cuda()
+            nxt = fn(cm, xi, sig[i:i + 2], disable=True)
+            steps.append(errs(nxt, golden_traj_small[f"traj.{tag}.x{i + 1}"])[1])
+    parity_log(f"traj.{tag}[{precision}]", free_run_e_max=e_max, free_run_e_l2=e_l2, per_step_e_l2=steps)
+    print(f"trajectory {tag} [{precision}]: free-run max {e_max:.3e} l2 {e_l2:.3e}; per step l2 {['%.2e' % v for v in steps]}")
+    assert e_l2 <= TRAJ_FREE[tag][0 if precision == "fp32" else 1]
+    for v in steps:
+        assert v <= (TOL_FP32 if precision == "fp32" else TRAJ_STEP_BF16)
 
 
 @pytest.mark.parametrize("sampler", ["euler", "heun"])
@@ -212,13 +226,7 @@ def test_unet_module_autograd(tiny_model, golden_small):
     assert torch.isfinite(g2).all() and g2.abs().max() > 0
 
 
-@pytest.mark.parametrize("ot", ["dwt", "dct"])
-@pytest.mark.parametrize("sigma", I.V2_SIGMAS)
-def test_v2_denoiser_type_II_guidance(ot, sigma, golden_v2):
-    """BASELINE configs[4]: ConditionOpenAIDenoiserV2 on OpenAIDenoiserV2 (out_cov head fused into the UNet engine, continuous t,
-    no clamp), type-II guidance x0 + W(theta * W^T v) with the per-pixel transform-domain variance below mle_sigma_thres = 1.0
-    (batched on-device CG) and the closed form above it - vs the reference's own output (golden_v2)."""
-    from condition.condition import ConditionOpenAIDenoiserV2
+def _v2_denoiser(ot, precision):
     from guided_diffusion.script_util import create_gaussian_diffusion
     from guided_diffusion.unet import UNetModel
     from k_diffusion.external import OpenAIDenoiserV2
@@ -229,13 +237,54 @@ def test_v2_denoiser_type_II_guidance(ot, sigma, golden_v2):
                       attention_resolutions=cfg.attention_ds(), channel_mult=cfg.resolved_channel_mult(), num_head_channels=64,
                       use_scale_shift_norm=True, resblock_updown=True)
     model.load_state_dict(sd, strict=True)
+    model.precision = precision
     model = model.eval().cuda()
-    diffusion = create_gaussian_diffusion(learn_sigma=True)
-    den = OpenAIDenoiserV2(model, diffusion, device="cuda", ortho_tf_type=ot).cuda()
+    den = OpenAIDenoiserV2(model, create_gaussian_diffusion(learn_sigma=True), device="cuda", ortho_tf_type=ot).cuda()
     cov_w, cov_b = I.v2_out_cov(seed=9)
     with torch.no_grad():
         den.out_cov.weight.copy_(cov_w)
         den.out_cov.bias.copy_(cov_b)
+    return den
+
+
+V2_VJP_CASES = [("dwt", "I", {}), ("dct", "I", {}), (None, "I", {}), ("dwt", "pgdm", {}), ("dwt", "dps", {"zeta": 1.0})]
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("case", V2_VJP_CASES, ids=lambda c: f"{c[0]}-{c[1]}")
+@pytest.mark.parametrize("sigma", I.V2_SIGMAS)
+def test_v2_denoiser_vjp_guidance(case, sigma, precision, golden_v2, parity_log):
+    """a11: guidance that differentiates through the v2 (DWT-Var) denoiser - type I (the default of
+    sample_condition_openai_v2.py:86), PiGDM and DPS (condition.py:140-174 on :287-300) - vs the reference's own output."""
+    from condition.condition import ConditionOpenAIDenoiserV2
+    ot, guidance, extra = case
+    den = _v2_denoiser(ot, precision)
+    op = make_op("gaussian_blur", 64)
+    y = torch.from_numpy(golden_v2["v2.y"]).cuda()
+    cm = ConditionOpenAIDenoiserV2(denoiser=den, operator=op, measurement=(y, y.reshape(1, -1)), guidance=guidance, device="cuda",
+                                   mle_sigma_thres=1.0, ortho_tf_type=ot, **extra).eval()
+    xt = I.xt(64, sigma, seed=21).cuda()
+    hat = cm(xt, torch.tensor([sigma]).cuda())
+    assert torch.isfinite(hat).all()
+    e_max, e_l2 = errs(hat, golden_v2[f"v2.{ot}.{guidance}.{sigma}.hat"])
+    check_eval(f"v2.{ot}.{guidance}.{sigma}", precision, min(sigma, 1.5), e_max, e_l2, parity_log)
+    y2 = y.expand(2, -1, -1, -1).contiguous()
+    cm2 = ConditionOpenAIDenoiserV2(denoiser=den, operator=op, measurement=(y2, y2.reshape(2, -1)), guidance=guidance, device="cuda",
+                                    mle_sigma_thres=1.0, ortho_tf_type=ot, **extra).eval()
+    hat2 = cm2(xt.expand(2, -1, -1, -1).contiguous(), torch.full((2,), sigma).cuda())
+    b_max, b_l2 = errs(hat2[1:2], hat)
+    check_eval(f"v2.{ot}.{guidance}.{sigma}.batch2_vs_single", precision, min(sigma, 1.5), b_max, b_l2, parity_log)
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("ot", ["dwt", "dct"])
+@pytest.mark.parametrize("sigma", I.V2_SIGMAS)
+def test_v2_denoiser_type_II_guidance(ot, sigma, precision, golden_v2, parity_log):
+    """BASELINE configs[4]: ConditionOpenAIDenoiserV2 on OpenAIDenoiserV2 (out_cov head fused into the UNet engine, continuous t,
+    no clamp), type-II guidance x0 + W(theta * W^T v) with the per-pixel transform-domain variance below mle_sigma_thres = 1.0
+    (batched on-device CG) and the closed form above it - vs the reference's own output (golden_v2)."""
+    from condition.condition import ConditionOpenAIDenoiserV2
+    den = _v2_denoiser(ot, precision)
     op = make_op("gaussian_blur", 64)
     y = torch.from_numpy(golden_v2["v2.y"]).cuda()
     cm = ConditionOpenAIDenoiserV2(denoiser=den, operator=op, measurement=(y, y.reshape(1, -1)), guidance="II", device="cuda",
@@ -244,25 +293,25 @@ def test_v2_denoiser_type_II_guidance(ot, sigma, golden_v2):
     hat = cm(xt, torch.tensor([sigma]).cuda())
     assert torch.isfinite(hat).all()
     e_max, e_l2 = errs(hat, golden_v2[f"v2.{ot}.{sigma}.hat"])
-    print(f"v2 type-II {ot} sigma={sigma}: max {e_max:.3e} l2 {e_l2:.3e}")
-    assert e_max < 6e-2 and e_l2 < 3e-2      # one bf16 UNet forward, no VJP: the floor of the module docstring
+    check_eval(f"v2.{ot}.II.{sigma}", precision, min(sigma, 1.5), e_max, e_l2, parity_log)   # no VJP: well conditioned at any sigma
     # batch of 2 identical problems == the single problem
     y2 = y.expand(2, -1, -1, -1).contiguous()
     cm2 = ConditionOpenAIDenoiserV2(denoiser=den, operator=op, measurement=(y2, y2.reshape(2, -1)), guidance="II", device="cuda",
                                     mle_sigma_thres=1.0, ortho_tf_type=ot).eval()
     hat2 = cm2(xt.expand(2, -1, -1, -1).contiguous(), torch.full((2,), sigma).cuda())
-    assert errs(hat2[1:2], hat)[1] < 1e-2
+    b_max, b_l2 = errs(hat2[1:2], hat)
+    check_eval(f"v2.{ot}.II.{sigma}.batch2_vs_single", precision, min(sigma, 1.5), b_max, b_l2, parity_log)
 
 
+@pytest.mark.parametrize("precision", PRECISIONS)
 @pytest.mark.parametrize("case", I.STSL_CASES, ids=lambda c: f"{c[0]}-{c[1]}")
-def test_stsl_guidance(case, tiny_model, golden_stsl):
+def test_stsl_guidance(case, precision, tiny_models, golden_stsl, parity_log):
     """STSL (condition.py:185-208): DPS data term + Hutchinson second-order term, composed on the GPU from 1 + n UNet forward + VJP
     pairs, vs the reference's own output (tests/golden/make_golden_stsl.py) on the same probes eps (the reference's CPU draws are
-    injected through the _hutchinson_eps hook).  Tolerance as in the module docstring: the per-evaluation floor, or twice the
-    reference's own sensitivity to bf16 weight rounding where that is larger (sigma = 3 with eta sigma^4 weighting)."""
+    injected through the _hutchinson_eps hook).  Fixed tolerances of the module docstring (sigma = 3 with its eta sigma^4
+    weighting is one of the ill-conditioned bf16 cases)."""
     from condition.condition import ConditionOpenAIDenoiser
-    from oracle import guidance_ref
-    model, diffusion = tiny_model
+    model, diffusion = tiny_models(precision)
     opname, sigma, zeta, eta, n, seed = case
     op = make_op(opname, 64)
     kw = dict(zeta=zeta, eta=eta, num_hutchinson_samples=n)
@@ -279,22 +328,12 @@ def test_stsl_guidance(case, tiny_model, golden_stsl):
     gold = torch.as_tensor(golden_stsl[f"stsl.{opname}.{sigma}"])
     e_max, e_l2 = errs(hat, gold)
     frac = ((hat.cpu() - gold).abs() > 6e-2).float().mean().item()
-    cfg, sd_b = bf16_weight_oracle()
-    ref_op, meas = oracle_measurement(opname)
-    probe = guidance_ref.ConditionDenoiserRef(sd_b, cfg, ref_op, meas, "stsl", "pgdm", **kw)
-    torch.manual_seed(seed)
-    p = probe(I.xt(64, sigma, seed=21), torch.tensor([sigma]))
-    s_l2 = errs(p, gold)[1]
-    s_frac = ((p - gold).abs() > 6e-2).float().mean().item()
-    print(f"stsl {opname} sigma={sigma}: max {e_max:.3e} l2 {e_l2:.3e} frac>6e-2 {frac:.4f} | reference bf16-weight sensitivity l2 "
-          f"{s_l2:.3e} frac {s_frac:.4f}")
-    assert e_l2 <= max(3e-2, 2 * s_l2) and frac <= max(0.03, 3 * s_frac)
-    # the Hutchinson term is really there: the eta = 0 reference output is much further away than the tolerance
+    check_eval(f"stsl.{opname}.{sigma}", precision, sigma, e_max, e_l2, parity_log, frac_gt_6e2=frac)
+    # the Hutchinson term is really there: the eta = 0 reference output is much further away than the error
     assert errs(golden_stsl[f"stsl.{opname}.{sigma}.eta0"], gold)[1] > 3 * max(e_l2, 1e-2)
     # batch of 2 identical problems == the single problem
-    b_l2 = errs(run(2)[1:2], hat)[1]
-    print(f"   batch-of-2 vs single: l2 {b_l2:.3e}")
-    assert b_l2 <= max(1e-2, 2 * s_l2)
+    b_max, b_l2 = errs(run(2)[1:2], hat)
+    check_eval(f"stsl.{opname}.{sigma}.batch2_vs_single", precision, sigma, b_max, b_l2, parity_log)
 
 
 @pytest.mark.parametrize("case", I.EXTRA_SAMPLER_CASES, ids=lambda c: c[0])
