@@ -178,6 +178,7 @@ typedef struct kdip_op kdip_op;
 int kdip_op_create(const kdip_op_desc* d, kdip_op** out);   /* allocates + synchronises (setup only) */
 void kdip_op_destroy(kdip_op* op);
 int kdip_op_workspace_bytes(const kdip_op* op, int B, size_t* bytes);
+int kdip_op_side(const kdip_op* op);   /* image side S the operator was created for */
 /* operator.forward(data, noiseless = (noise == NULL)): y = A x + sigma_s * noise          measurements.py:103-111,139-148,
  * 178-188,211-226.  noise has y's shape (drawn by the caller, torch.randn_like in the reference). */
 int kdip_op_forward(const kdip_op* op, const float* x, const float* noise, float* y, int B, void* ws, size_t ws_bytes,
@@ -198,7 +199,9 @@ int kdip_mat_closed(const kdip_op* op, const float* y, const float* x0, const fl
                     size_t ws_bytes, kdip_stream_t s);
 /* CG mat for a per-element variance map theta_map [B,3,S,S] in the domain of transform `ot`  condition.py:325-346,359-384,412-437.
  * Batched on-device CG with scipy's semantics (x0 = 0, stop when ||r|| < tol*||b||, at most maxiter matvecs), per-image
- * convergence.  iters_out: HOST int[B] or NULL.  Polls convergence, i.e. synchronises the stream (not graph-capturable).
+ * convergence; alpha / beta / the convergence flags stay on the device.  iters_out: HOST int[B] or NULL.  The host polls the flags
+ * with a one-iteration lag through pinned snapshots owned by the handle (event waits: not graph-capturable; at most one surplus
+ * iteration is queued after the last image converged).  B <= 4096.
  * Returns KDIP_ENOTCONV (result still written, like the reference's warning) when an image hit maxiter. */
 int kdip_mat_cg(kdip_op* op, const float* y, const float* x0, const float* theta_map, int ot, float* mat, int B, float tol,
                 int maxiter, int* iters_out, void* ws, size_t ws_bytes, kdip_stream_t s);
@@ -332,6 +335,34 @@ int kdip_unet_schema_entry(const kdip_unet_arch* arch, int index, char* name_out
                            int* ndim);
 /* Pre-head feature [N, C0, S, S] fp32 of the last forward (UNetModel.forward(return_feature=True), unet.py:665-666). */
 int kdip_unet_feature(kdip_unet* u, int N, float* feat, kdip_stream_t s);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Fused guided model evaluation - the fast path of SURVEY.md 8(b) "Denoiser API": ConditionDenoiser.forward
+ * (condition/condition.py:83-174) over ConditionOpenAIDenoiser.uncond_pred (:231-274) for every branch with a closed-form
+ * mat solver: hat_x0 = clip(x0 + coef * J^T v, -1, 1).  One call enqueues UNet forward, p_mean_variance epilogue, mat solver
+ * (or the DPS residual gradient), VJP seed, UNet input-VJP and the combine on `s` out of the caller's workspace: no allocation,
+ * no synchronisation, capturable as ONE CUDA graph per (guidance, B).  `cfg` is copied to the device with cudaMemcpyAsync (under
+ * capture a memcpy node: keep it in pinned host memory, update it and replay for the next sigma).  sigma is uniform over the
+ * batch, as inside a sampler call.  The per-pixel covariance + CG branch (sigma < mle_sigma_thres with Convert / TMPD / DWT-Var)
+ * is NOT covered: it polls convergence on the host - use kdip_unet_* + kdip_mat_cg + kdip_guidance_combine.
+ * ------------------------------------------------------------------------------------------------------------ */
+#define KDIP_GUIDE_UNCOND 0  /* hat_x0 = x0_mean                                                  condition.py:104-106 */
+#define KDIP_GUIDE_TYPE_I 1  /* x0 + sigma^2 J^T mat(theta), scalar theta (Convert above thres, Analytic, ...)   :167-174 */
+#define KDIP_GUIDE_PGDM 2    /* theta = r^2: x0 + sigma^2 r^2 J^T mat                                             :150-157 */
+#define KDIP_GUIDE_DPS 3     /* x0 + sigma^2 zeta J^T A^T r / ||r||                                               :140-148 */
+#define KDIP_GUIDE_DIFFPIR 4 /* x0 + theta mat(theta), theta = sigma^2 / lambda (no VJP)                          :159-165 */
+typedef struct {
+  int guidance;         /* KDIP_GUIDE_*                                                                                   */
+  float sigma;          /* noise level of this evaluation                                                                 */
+  float t_model;        /* timestep fed to the UNet: timestep_map[floor(sigma_to_t(sigma))] (condition.py:233, respace.py:123-128) */
+  float theta;          /* scalar x0 variance handed to the mat solver (r^2, the Analytic table entry, sigma^2/lambda)    */
+  float zeta;           /* DPS step size                                                                                  */
+  kdip_pmv_scalars sc;  /* schedule constants at that integer timestep (c_in included)                                    */
+} kdip_guided_cfg;
+int kdip_guided_eval_workspace_bytes(kdip_unet* u, const kdip_op* op, int B, size_t* bytes);
+/* x [B,3,S,S] (unscaled x_t), y: the measurement (operator.forward's shape) -> hat_x0 [B,3,S,S]. */
+int kdip_guided_eval(kdip_unet* u, kdip_op* op, const kdip_guided_cfg* cfg, const float* x, const float* y, float* hat_x0, int B,
+                     void* ws, size_t ws_bytes, kdip_stream_t s);
 
 /* ------------------------------------------------------------------------------------------------------------
  * UNet building blocks, exported for per-layer parity tests (tests/test_layers_gpu.py).  Activations are bf16 NHWC.

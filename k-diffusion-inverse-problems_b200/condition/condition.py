@@ -112,6 +112,9 @@ class ConditionDenoiser(nn.Module):
         if g in ("dps+mle", "pgdm+mle", "stsl+mle"):
             g = "I" if sig < self.mle_sigma_thres else g.split("+")[0]
         x = x.detach().contiguous().float()
+        fused = self._fused_eval(g, x, sig)
+        if fused is not None:
+            return fused
         if g == "uncond":
             x0_mean = self.uncond_pred(x, sigma)[0]
             return ops.guidance_combine(x0_mean, x0_mean, None, _dev([0.0] * B, x.device))
@@ -130,6 +133,10 @@ class ConditionDenoiser(nn.Module):
         if g == "autoI":
             raise NotImplementedError(f"guidance '{self.guidance}' is outside the kdip hot path (SURVEY.md §2 #2)")
         raise ValueError(f"Invalid guidance type: '{self.guidance}'.")
+
+    def _fused_eval(self, g, x, sig):
+        """One kdip_guided_eval call for the branches it covers (subclasses decide); None -> the composed path below."""
+        return None
 
     def _dps_guidance_impl(self, x, sigma):
         """condition.py:140-148: x0 - sigma^2 zeta grad_x ||y - A(x0)||_2  (per-image norm; equals the reference at B = 1)."""
@@ -232,6 +239,66 @@ class ConditionOpenAIDenoiser(ConditionDenoiser):
             for key in self.recon_mse.keys():
                 self.recon_mse[key] = self.recon_mse[key].to(self.device)
             self._recon_sigmas_host = self.recon_mse['sigmas'].detach().float().cpu().numpy()
+            self._recon_mse_host = self.recon_mse['mse_list'].detach().float().cpu().numpy()
+
+    def _timestep(self, sig):
+        """(t_int, t_model) for a host sigma: condition.py:233 (.long() truncates), respace.py:123-128."""
+        t_int = int(self.denoiser.sigma_to_t_host(float(sig)))
+        tm = getattr(self.diffusion, "timestep_map", None)
+        t_model = tm[t_int] if tm is not None else t_int
+        if getattr(self.diffusion, "rescale_timesteps", False):
+            orig = getattr(self.diffusion, "original_num_steps", self.diffusion.num_timesteps)
+            t_model = float(t_model) * (1000.0 / orig)
+        return t_int, t_model
+
+    def _fused_eval(self, g, x, sig):
+        """kdip_guided_eval (include/kdip.h): the whole evaluation as one library call / one CUDA-graph replay whenever the mat
+        solver is a built-in closed form: guidance uncond / pgdm / dps / diffpir, and type I with a scalar x0 variance (Convert
+        above mle_sigma_thres, Analytic, pgdm, dps, diffpir covariance types).  KDIP_FUSED_EVAL=0 selects the composed path."""
+        import os
+        if os.environ.get("KDIP_FUSED_EVAL", "1") == "0" or self.ortho_tf_type is not None:
+            return None
+        handle = getattr(self.operator, "handle", None)
+        if handle is None or self.mat_solver is not _BUILTIN_SOLVERS.get(getattr(self.operator, "name", None)):
+            return None
+        sig = np.float32(sig)
+        r2 = float(sig ** 2 / (1 + sig ** 2))
+        mle = bool(sig < self.mle_sigma_thres)
+        theta, zeta = 0.0, 0.0
+        if g == "pgdm":
+            theta = r2
+        elif g == "diffpir":
+            if self.lambda_ is None:
+                return None
+            theta = float(sig ** 2 / np.float32(self.lambda_))
+        elif g == "dps":
+            if self.zeta is None:
+                return None
+            zeta = float(np.float32(self.zeta))
+        elif g == "I":
+            ct = self.x0_cov_type
+            if ct == "convert" and not mle:
+                theta = r2
+            elif ct == "analytic" and self.recon_mse is not None:
+                theta = float(self._recon_mse_host.reshape(-1)[int(np.abs(self._recon_sigmas_host - sig).argmin())]) if mle else r2
+            elif ct == "pgdm":
+                theta = r2
+            elif ct == "dps":
+                theta = 0.0
+            elif ct == "diffpir" and self.lambda_ is not None:
+                theta = float(sig ** 2 / np.float32(self.lambda_))
+            else:
+                return None                       # per-pixel covariance (Convert below the threshold, TMPD): CG path
+        elif g != "uncond":
+            return None
+        eng = self.inner_model.engine()
+        fe = getattr(self, "_fused", None)
+        if fe is None or fe.engine is not eng or fe.handle is not handle:
+            fe = self._fused = ops.FusedGuidedEval(eng, handle)
+        t_int, t_model = self._timestep(sig)
+        c_in = float(np.float32(1) / np.sqrt(sig * sig + np.float32(1)))
+        sc = ops.pmv_scalars_one(self.diffusion, t_int, c_in)
+        return fe(g, float(sig), t_model, theta, zeta, sc, x, self._y_for(x.shape[0]))
 
     def uncond_pred(self, x, sigma):
         """-> (x0_mean [B,3,H,W], x0_var, theta0_var); x0_var is [B] (per-image scalar) or a [B,3,H,W] map."""
@@ -239,12 +306,8 @@ class ConditionOpenAIDenoiser(ConditionDenoiser):
         sig_list = _host_sigma(sigma, B)
         sig = np.float32(_uniform(sig_list))
         c_in = [float(np.float32(1) / np.sqrt(sig * sig + np.float32(1)))] * B           # external.py:97-100
-        t_int = [int(self.denoiser.sigma_to_t_host(float(sig)))] * B                     # condition.py:233: .long() truncates
-        tm = getattr(self.diffusion, "timestep_map", None)
-        t_model = [tm[t] for t in t_int] if tm is not None else t_int                    # respace.py:123-128
-        if getattr(self.diffusion, "rescale_timesteps", False):                          # respace.py:125-126 / gaussian_diffusion.py:254
-            orig = getattr(self.diffusion, "original_num_steps", self.diffusion.num_timesteps)
-            t_model = [float(t) * (1000.0 / orig) for t in t_model]
+        t1, tm1 = self._timestep(sig)
+        t_int, t_model = [t1] * B, [tm1] * B
         c_in_dev = _dev(c_in, x.device)
         eng = self.inner_model.engine()
         out = eng.forward(x, _dev([float(t) for t in t_model], x.device), x_scale=c_in_dev)
@@ -379,3 +442,7 @@ def motion_blur_mat(operator, y, x0_mean, theta0_var, ortho_tf=OrthoTransform())
 def super_resolution_mat(operator, y, x0_mean, theta0_var, ortho_tf=OrthoTransform()):
     """condition.py:401-439."""
     return _solve(operator, y, x0_mean, theta0_var, ortho_tf)
+
+
+# the solvers shipped here: ConditionDenoiser._fused_eval takes the one-call path only while the registry still holds them
+_BUILTIN_SOLVERS = dict(__MAT_SOLVER__)

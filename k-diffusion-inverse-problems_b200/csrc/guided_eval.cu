@@ -1,0 +1,133 @@
+// kdip_guided_eval: ONE call = one guided model evaluation of the sampling loop (condition/condition.py:83-174 on top of
+// ConditionOpenAIDenoiser.uncond_pred, :231-274) for the branches that need no iterative solver:
+//     UNet forward -> p_mean_variance epilogue -> mat (closed form, scalar x0 variance) or DPS residual gradient
+//     -> clamp / scaling VJP seed -> UNet input-VJP -> hat_x0 = clip(x0 + coef (c_in g + direct), -1, 1)
+// Everything is enqueued on the caller's stream from the caller's workspace: no allocation, no synchronisation, so the whole
+// evaluation can be captured into a single CUDA graph per (configuration, batch).  The per-evaluation scalars travel in a small
+// host struct that is copied to the device with cudaMemcpyAsync: under capture that is a memcpy NODE, i.e. a replay re-reads the
+// (pinned) host struct - update it, replay, and the same graph serves every sigma of the schedule.
+// The per-pixel-covariance / CG branch (condition.py:325-346,359-384,412-437) polls convergence on the host and stays with the
+// individually exported pieces (kdip_mat_cg etc.), which is also what user-registered operators / mat solvers use.
+#include "kdip_common.cuh"
+
+namespace kdip {
+
+struct GeWs {
+  void *unet_ws, *op_ws;
+  size_t unet_bytes, op_bytes;
+  float *out6, *x0, *mat, *seed, *direct, *grad;
+  kdip_guided_cfg* cfg;
+  kdip_pmv_scalars* sc;
+  float *c_in, *t, *theta, *coef, *norm;
+};
+
+struct Bump {
+  char* base;
+  size_t cur = 0;
+  void* take(size_t bytes) {
+    const size_t o = cur;
+    cur += (bytes + 255) & ~(size_t)255;
+    return base ? (void*)(base + o) : nullptr;
+  }
+};
+
+static int plan(kdip_unet* u, const kdip_op* op, int B, void* base, size_t* total, GeWs* w) {
+  size_t ub = 0, ob = 0;
+  int rc = kdip_unet_workspace_bytes(u, B, &ub);
+  if (rc) return rc;
+  rc = kdip_op_workspace_bytes(op, B, &ob);
+  if (rc) return rc;
+  const int S = kdip_op_side(op);
+  const size_t plane = (size_t)B * 3 * S * S * sizeof(float);
+  Bump a{(char*)base};
+  w->unet_bytes = ub; w->op_bytes = ob;
+  w->unet_ws = a.take(ub);
+  w->op_ws = a.take(ob);
+  w->out6 = (float*)a.take(2 * plane);
+  w->x0 = (float*)a.take(plane);
+  w->mat = (float*)a.take(plane);
+  w->seed = (float*)a.take(2 * plane);
+  w->direct = (float*)a.take(plane);
+  w->grad = (float*)a.take(plane);
+  w->cfg = (kdip_guided_cfg*)a.take(sizeof(kdip_guided_cfg));
+  w->sc = (kdip_pmv_scalars*)a.take((size_t)B * sizeof(kdip_pmv_scalars));
+  w->c_in = (float*)a.take((size_t)B * 4);
+  w->t = (float*)a.take((size_t)B * 4);
+  w->theta = (float*)a.take((size_t)B * 4);
+  w->coef = (float*)a.take((size_t)B * 4);
+  w->norm = (float*)a.take((size_t)B * 4);
+  *total = a.cur;
+  return KDIP_OK;
+}
+
+// broadcast the evaluation's scalars (uniform over the batch inside a sampler call) into the per-image device arrays
+__global__ void ge_fill_kernel(const kdip_guided_cfg* __restrict__ cfg, kdip_pmv_scalars* __restrict__ sc, float* __restrict__ c_in,
+                               float* __restrict__ t, float* __restrict__ theta, float* __restrict__ coef, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const kdip_guided_cfg c = *cfg;
+  sc[b] = c.sc;
+  c_in[b] = c.sc.c_in;
+  t[b] = c.t_model;
+  theta[b] = c.theta;
+  const float s2 = c.sigma * c.sigma;
+  float k = 0.f;
+  if (c.guidance == KDIP_GUIDE_TYPE_I) k = s2;                                   // condition.py:173
+  else if (c.guidance == KDIP_GUIDE_PGDM) k = s2 * c.theta;                      // :155-156 (theta = r^2)
+  else if (c.guidance == KDIP_GUIDE_DIFFPIR) k = c.theta;                        // :164
+  coef[b] = k;
+}
+// DPS: coef[b] = sigma^2 zeta / ||r_b||                                          condition.py:145-147
+__global__ void ge_dps_coef_kernel(const kdip_guided_cfg* __restrict__ cfg, const float* __restrict__ norm, float* __restrict__ coef, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) coef[b] = cfg->sigma * cfg->sigma * cfg->zeta / norm[b];
+}
+
+}  // namespace kdip
+
+using namespace kdip;
+
+extern "C" int kdip_guided_eval_workspace_bytes(kdip_unet* u, const kdip_op* op, int B, size_t* bytes) {
+  KDIP_REQUIRE(u && op && bytes && B > 0, KDIP_EINVAL, "guided_eval_workspace_bytes: bad argument");
+  GeWs w;
+  return plan(u, op, B, nullptr, bytes, &w);
+}
+
+extern "C" int kdip_guided_eval(kdip_unet* u, kdip_op* op, const kdip_guided_cfg* cfg, const float* x, const float* y, float* hat_x0,
+                                int B, void* ws, size_t ws_bytes, kdip_stream_t stream) {
+  KDIP_REQUIRE(u && op && cfg && x && y && hat_x0 && B > 0, KDIP_EINVAL, "guided_eval: bad argument");
+  KDIP_REQUIRE(cfg->guidance >= KDIP_GUIDE_UNCOND && cfg->guidance <= KDIP_GUIDE_DIFFPIR, KDIP_EINVAL, "guided_eval: unknown guidance %d",
+               cfg->guidance);
+  KDIP_REQUIRE(ws != nullptr && ((uintptr_t)ws % 256) == 0, KDIP_EALIGN, "guided_eval: workspace must be 256-byte aligned");
+  GeWs w;
+  size_t need = 0;
+  int rc = plan(u, op, B, ws, &need, &w);
+  if (rc) return rc;
+  KDIP_REQUIRE(need <= ws_bytes, KDIP_ENOMEM, "guided_eval: workspace too small: need %zu bytes, got %zu", need, ws_bytes);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int S = kdip_op_side(op), HW = S * S, CHW = 3 * HW;
+  const int g = cfg->guidance;
+  KDIP_CUDA(cudaMemcpyAsync(w.cfg, cfg, sizeof(kdip_guided_cfg), cudaMemcpyHostToDevice, st));
+  ge_fill_kernel<<<(B + 127) / 128, 128, 0, st>>>(w.cfg, w.sc, w.c_in, w.t, w.theta, w.coef, B);
+  KDIP_LAUNCH_CHECK();
+  rc = kdip_unet_forward(u, x, w.c_in, w.t, B, w.out6, nullptr, w.unet_ws, w.unet_bytes, stream);
+  if (rc) return rc;
+  rc = kdip_pmv_epilogue(w.out6, x, w.sc, w.x0, nullptr, 0, B, HW, stream);
+  if (rc) return rc;
+  if (g == KDIP_GUIDE_UNCOND) return kdip_guidance_combine(w.x0, w.x0, nullptr, w.coef, nullptr, hat_x0, B, CHW, stream);
+  if (g == KDIP_GUIDE_DPS) {
+    rc = kdip_dps_grad(op, y, w.x0, w.mat, w.norm, B, w.op_ws, w.op_bytes, stream);
+    if (rc) return rc;
+    ge_dps_coef_kernel<<<(B + 127) / 128, 128, 0, st>>>(w.cfg, w.norm, w.coef, B);
+    KDIP_LAUNCH_CHECK();
+  } else {
+    rc = kdip_mat_closed(op, y, w.x0, w.theta, w.mat, B, w.op_ws, w.op_bytes, stream);
+    if (rc) return rc;
+    if (g == KDIP_GUIDE_DIFFPIR) return kdip_guidance_combine(w.x0, w.mat, nullptr, w.coef, nullptr, hat_x0, B, CHW, stream);
+  }
+  rc = kdip_pmv_vjp_seed(w.x0, w.mat, w.sc, w.seed, w.direct, B, HW, stream);
+  if (rc) return rc;
+  rc = kdip_unet_vjp(u, w.seed, B, w.grad, w.unet_ws, w.unet_bytes, stream);
+  if (rc) return rc;
+  return kdip_guidance_combine(w.x0, w.grad, w.direct, w.coef, w.c_in, hat_x0, B, CHW, stream);
+}

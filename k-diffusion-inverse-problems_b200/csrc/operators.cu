@@ -216,40 +216,20 @@ __global__ void __launch_bounds__(OP_THREADS) dot_partial_kernel(const float* __
   if (threadIdx.x == 0) part[img * CG_NBLK + blockIdx.x] = acc;
 }
 
+// Per-image CG scalars, all resident on the device.  rho / done are double-buffered by iteration parity so that the kernel that
+// publishes iteration k's values (cg_p_kernel, one thread per image) never races with the CTAs of the same launch still reading
+// iteration k-1's: alpha and beta are formed inside the vector kernels from the reduction partials - no scalar kernels, no host.
 struct CgState {
-  float *rho, *pq, *alpha, *beta, *atol2;   // [B]
-  int *done, *iters;                        // [B]
+  float *rho[2];      // [B] ||r||^2 entering the iteration
+  int *done[2];       // [B] converged (frozen) flags
+  float *atol2;       // [B] (tol ||b||)^2
+  int *iters;         // [B]
 };
 
 __device__ __forceinline__ float sum_partials(const float* part, int img) {
   float s = 0.f;
   for (int i = 0; i < CG_NBLK; ++i) s += part[(size_t)img * CG_NBLK + i];
   return s;
-}
-
-// stage 0: after ||b||^2 partials; stage 1: after p.q partials; stage 2: after ||r_new||^2 partials
-__global__ void cg_scalar_kernel(int stage, const float* __restrict__ part, CgState st, float tol, int B) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
-  const float v = sum_partials(part, b);
-  if (stage == 0) {
-    st.rho[b] = v;
-    st.atol2[b] = tol * tol * v;
-    st.done[b] = (v == 0.f) ? 1 : 0;   // b == 0 -> x = 0 (scipy returns immediately)
-    st.iters[b] = 0;
-    st.beta[b] = 0.f;
-    st.alpha[b] = 0.f;
-  } else if (stage == 1) {
-    st.pq[b] = v;
-    st.alpha[b] = st.rho[b] / v;
-  } else {
-    if (!st.done[b]) {
-      st.beta[b] = v / st.rho[b];
-      st.rho[b] = v;
-      st.iters[b] += 1;
-      if (v < st.atol2[b]) st.done[b] = 1;
-    }
-  }
 }
 
 // x = 0 ; p = r ; partial ||r||^2
@@ -266,15 +246,24 @@ __global__ void __launch_bounds__(OP_THREADS) cg_init_kernel(const float* __rest
   acc = block_sum(acc);
   if (threadIdx.x == 0) part[img * CG_NBLK + blockIdx.x] = acc;
 }
-// x += alpha p ; r -= alpha q ; partial ||r||^2   (frozen once the image converged)
+// after ||b||^2 partials: rho, tolerance, b == 0 -> x = 0 (scipy returns immediately)
+__global__ void cg_begin_kernel(const float* __restrict__ part, CgState st, float tol, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float v = sum_partials(part, b);
+  st.rho[0][b] = v;
+  st.atol2[b] = tol * tol * v;
+  st.done[0][b] = (v == 0.f) ? 1 : 0;
+  st.iters[b] = 0;
+}
+// alpha = rho / (p.q) from the partials of the preceding dot; x += alpha p ; r -= alpha q ; partial ||r||^2 (frozen once converged)
 __global__ void __launch_bounds__(OP_THREADS) cg_update_kernel(float* __restrict__ x, float* __restrict__ r, const float* __restrict__ p,
-                                                                const float* __restrict__ q, CgState st, float* __restrict__ part,
-                                                                size_t n) {
+                                                                const float* __restrict__ q, CgState st, int cur,
+                                                                const float* __restrict__ part_pq, float* __restrict__ part_rr, size_t n) {
   const size_t img = blockIdx.y;
-  const bool frozen = st.done[img] != 0;
-  const float alpha = st.alpha[img];
   float acc = 0.f;
-  if (!frozen) {
+  if (!st.done[cur][img]) {
+    const float alpha = st.rho[cur][img] / sum_partials(part_pq, (int)img);
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
       const size_t o = img * n + i;
       x[o] = x[o] + alpha * p[o];
@@ -284,13 +273,24 @@ __global__ void __launch_bounds__(OP_THREADS) cg_update_kernel(float* __restrict
     }
   }
   acc = block_sum(acc);
-  if (threadIdx.x == 0) part[img * CG_NBLK + blockIdx.x] = acc;
+  if (threadIdx.x == 0) part_rr[img * CG_NBLK + blockIdx.x] = acc;
 }
-// p = r + beta p
-__global__ void __launch_bounds__(OP_THREADS) cg_p_kernel(float* __restrict__ p, const float* __restrict__ r, CgState st, size_t n) {
+// beta = ||r_new||^2 / rho ; p = r + beta p ; block 0 of each image publishes rho / done / iters of the next iteration
+__global__ void __launch_bounds__(OP_THREADS) cg_p_kernel(float* __restrict__ p, const float* __restrict__ r, CgState st, int cur,
+                                                           const float* __restrict__ part_rr, size_t n) {
   const size_t img = blockIdx.y;
-  if (st.done[img]) return;
-  const float beta = st.beta[img];
+  const int nxt = cur ^ 1;
+  if (st.done[cur][img]) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) { st.done[nxt][img] = 1; st.rho[nxt][img] = st.rho[cur][img]; }
+    return;
+  }
+  const float rr = sum_partials(part_rr, (int)img);
+  const float beta = rr / st.rho[cur][img];
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    st.rho[nxt][img] = rr;
+    st.iters[img] += 1;
+    st.done[nxt][img] = (rr < st.atol2[img]) ? 1 : 0;
+  }
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const size_t o = img * n + i;
     p[o] = r[o] + beta * p[o];
@@ -329,10 +329,14 @@ struct kdip_op {
   // Resizer tables (forward gather + CSR of the adjoint), identical for both axes of a square image
   float* rs_w = nullptr; int* rs_idx = nullptr; int rs_taps = 0;
   int* rt_ptr = nullptr; int* rt_o = nullptr; float* rt_w = nullptr;
-  int* done_host = nullptr;  // pinned, for the CG convergence poll
-  int done_cap = 0;
+  // CG convergence poll: pinned host snapshots of the device flags (two slots: the host reads iteration k-1's while iteration k
+  // is already queued) + the iteration counts, and the events that guard them.  Allocated by kdip_op_create, never afterwards.
+  int* done_host = nullptr;  // [3][kCgMaxBatch]
+  cudaEvent_t poll_ev[2] = {nullptr, nullptr};
   std::vector<void*> owned;
 };
+
+static constexpr int kCgMaxBatch = 4096;
 
 static bool is_blur(const kdip_op* op) { return op->kind == KDIP_OP_GAUSSIAN_BLUR || op->kind == KDIP_OP_MOTION_BLUR; }
 
@@ -340,6 +344,8 @@ extern "C" void kdip_op_destroy(kdip_op* op) {
   if (!op) return;
   for (void* p : op->owned) cudaFree(p);
   if (op->done_host) cudaFreeHost(op->done_host);
+  for (int i = 0; i < 2; ++i)
+    if (op->poll_ev[i]) cudaEventDestroy(op->poll_ev[i]);
   delete op;
 }
 
@@ -364,6 +370,8 @@ extern "C" int kdip_op_create(const kdip_op_desc* d, kdip_op** out) {
 #define TRY(x) do { int _r = (x); if (_r != KDIP_OK) return fail(_r); } while (0)
 #define TRYC(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return fail(::kdip::cuda_fail(_e, #x, __FILE__, __LINE__)); } while (0)
   const int S = op->S, Sh = S / 2 + 1;
+  TRYC(cudaMallocHost((void**)&op->done_host, (size_t)3 * kCgMaxBatch * sizeof(int)));
+  for (int i = 0; i < 2; ++i) TRYC(cudaEventCreateWithFlags(&op->poll_ev[i], cudaEventDisableTiming));
   if (d->kind == KDIP_OP_INPAINTING) {
     if (!d->mask) { set_error("op_create: inpainting needs a mask"); return fail(KDIP_EINVAL); }
     TRY(op_alloc(op, (size_t)3 * S * S * 4, (void**)&op->mask));
@@ -440,7 +448,7 @@ struct OpWs {
   float2 *specA, *specB;
   float *full[6];        // [B*3][S][S] scratch planes
   float *small_[5];      // [B*3][s][s] (SR)
-  float *part;           // [B][CG_NBLK]
+  float *part, *part2;   // [B][CG_NBLK] partial sums of p.q and of ||r||^2
   CgState st;
   void* dct;             // DCT matrix + temp
 };
@@ -453,12 +461,15 @@ static size_t plan_ws(const kdip_op* op, int B, void* base, size_t cap, OpWs* w)
   for (int i = 0; i < 6; ++i) w->full[i] = a.take<float>(planes * S * S);
   for (int i = 0; i < 5; ++i) w->small_[i] = a.take<float>(planes * s * s);
   w->part = a.take<float>((size_t)B * CG_NBLK);
-  w->st.rho = a.take<float>(B); w->st.pq = a.take<float>(B); w->st.alpha = a.take<float>(B);
-  w->st.beta = a.take<float>(B); w->st.atol2 = a.take<float>(B);
-  w->st.done = a.take<int>(B); w->st.iters = a.take<int>(B);
+  w->part2 = a.take<float>((size_t)B * CG_NBLK);
+  for (int i = 0; i < 2; ++i) { w->st.rho[i] = a.take<float>(B); w->st.done[i] = a.take<int>(B); }
+  w->st.atol2 = a.take<float>(B);
+  w->st.iters = a.take<int>(B);
   w->dct = a.take<char>(dct_workspace_bytes((int)planes, (int)S));
   return a.cur;
 }
+
+extern "C" int kdip_op_side(const kdip_op* op) { return op ? op->S : 0; }
 
 extern "C" int kdip_op_workspace_bytes(const kdip_op* op, int B, size_t* bytes) {
   KDIP_REQUIRE(op && bytes && B > 0, KDIP_EINVAL, "op_workspace_bytes: bad argument");
@@ -709,12 +720,7 @@ extern "C" int kdip_mat_cg(kdip_op* op, const float* y, const float* x0, const f
   OpWs w;
   int rc = get_ws(op, B, ws, ws_bytes, &w);
   if (rc) return rc;
-  if (op->done_cap < B) {
-    if (op->done_host) cudaFreeHost(op->done_host);
-    op->done_host = nullptr;
-    KDIP_CUDA(cudaMallocHost((void**)&op->done_host, (size_t)2 * B * sizeof(int)));
-    op->done_cap = B;
-  }
+  KDIP_REQUIRE(B <= kCgMaxBatch, KDIP_ESHAPE, "mat_cg: batch %d exceeds the poll buffer (%d images)", B, kCgMaxBatch);
   const int planes = B * 3, S = op->S, s_ = op->s;
   const bool sr = op->kind == KDIP_OP_SUPER_RESOLUTION;
   float sig = op->sigma_s < 1e-3f ? 1e-3f : op->sigma_s;
@@ -787,35 +793,49 @@ extern "C" int kdip_mat_cg(kdip_op* op, const float* y, const float* x0, const f
   }
   if (rc) return rc;
   dim3 g(CG_NBLK, B);
-  cg_init_kernel<<<g, OP_THREADS, 0, st>>>(r, xs, p, w.part, n);
+  cg_init_kernel<<<g, OP_THREADS, 0, st>>>(r, xs, p, w.part2, n);
   KDIP_LAUNCH_CHECK();
-  const int sb = (B + 127) / 128;
-  cg_scalar_kernel<<<sb, 128, 0, st>>>(0, w.part, w.st, tol, B);
+  cg_begin_kernel<<<(B + 127) / 128, 128, 0, st>>>(w.part2, w.st, tol, B);
   KDIP_LAUNCH_CHECK();
+  // Iteration k reads rho / done slot k & 1 and publishes slot (k + 1) & 1.  The host never waits for the iteration it has just
+  // queued: after queueing iteration k it snapshots that iteration's flags (async copy + event) and inspects the snapshot of
+  // iteration k - 1, so the GPU always has one iteration of work queued behind the one being polled and at most one surplus
+  // iteration (frozen images: its vector kernels return immediately) runs after the last image converged.
   bool all_done = false;
-  for (int it = 0; it < maxiter; ++it) {
+  int* flags[2] = {op->done_host, op->done_host + kCgMaxBatch};
+  auto inspect = [&](int slot) {
+    bool d = true;
+    for (int b = 0; b < B; ++b) d = d && (flags[slot][b] != 0);
+    return d;
+  };
+  int it = 0;
+  for (; it < maxiter && !all_done; ++it) {
+    const int cur = it & 1;
     rc = matvec(p, q);
     if (rc) return rc;
     dot_partial_kernel<<<g, OP_THREADS, 0, st>>>(p, q, w.part, n);
     KDIP_LAUNCH_CHECK();
-    cg_scalar_kernel<<<sb, 128, 0, st>>>(1, w.part, w.st, tol, B);
+    cg_update_kernel<<<g, OP_THREADS, 0, st>>>(xs, r, p, q, w.st, cur, w.part, w.part2, n);
     KDIP_LAUNCH_CHECK();
-    cg_update_kernel<<<g, OP_THREADS, 0, st>>>(xs, r, p, q, w.st, w.part, n);
+    cg_p_kernel<<<g, OP_THREADS, 0, st>>>(p, r, w.st, cur, w.part2, n);
     KDIP_LAUNCH_CHECK();
-    cg_scalar_kernel<<<sb, 128, 0, st>>>(2, w.part, w.st, tol, B);
-    KDIP_LAUNCH_CHECK();
-    KDIP_CUDA(cudaMemcpyAsync(op->done_host, w.st.done, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
-    KDIP_CUDA(cudaStreamSynchronize(st));
-    all_done = true;
-    for (int b = 0; b < B; ++b) all_done = all_done && (op->done_host[b] != 0);
-    if (all_done) break;
-    cg_p_kernel<<<g, OP_THREADS, 0, st>>>(p, r, w.st, n);
-    KDIP_LAUNCH_CHECK();
+    KDIP_CUDA(cudaMemcpyAsync(flags[cur], w.st.done[cur ^ 1], (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
+    KDIP_CUDA(cudaEventRecord(op->poll_ev[cur], st));
+    if (it > 0) {
+      KDIP_CUDA(cudaEventSynchronize(op->poll_ev[cur ^ 1]));
+      all_done = inspect(cur ^ 1);
+    }
+  }
+  if (!all_done && it > 0) {      // the last queued iteration has not been inspected yet
+    const int last = (it - 1) & 1;
+    KDIP_CUDA(cudaEventSynchronize(op->poll_ev[last]));
+    all_done = inspect(last);
   }
   if (iters_out) {
-    KDIP_CUDA(cudaMemcpyAsync(op->done_host + B, w.st.iters, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
+    int* ih = op->done_host + 2 * kCgMaxBatch;
+    KDIP_CUDA(cudaMemcpyAsync(ih, w.st.iters, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
     KDIP_CUDA(cudaStreamSynchronize(st));
-    for (int b = 0; b < B; ++b) iters_out[b] = op->done_host[B + b];
+    for (int b = 0; b < B; ++b) iters_out[b] = ih[b];
   }
   // mat = A^T u (inpainting: the solution itself, condition.py:346)
   const size_t tot = (size_t)B * nfull;

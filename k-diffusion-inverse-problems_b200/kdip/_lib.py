@@ -78,6 +78,12 @@ class PmvScalars(ctypes.Structure):
     _fields_ = [(n, ctypes.c_float) for n in ("c_in", "recip", "recipm1", "min_log", "max_log", "post_var", "coef1_sq")]
 
 
+class GuidedCfg(ctypes.Structure):
+    """kdip_guided_cfg (include/kdip.h)."""
+    _fields_ = [("guidance", ctypes.c_int), ("sigma", ctypes.c_float), ("t_model", ctypes.c_float), ("theta", ctypes.c_float),
+                ("zeta", ctypes.c_float), ("sc", PmvScalars)]
+
+
 class UNetProfile(ctypes.Structure):
     _fields_ = [("conv_ms", ctypes.c_float), ("other_ms", ctypes.c_float), ("total_ms", ctypes.c_float),
                 ("conv_flops", ctypes.c_double), ("conv_launches", ctypes.c_int), ("other_steps", ctypes.c_int)]

@@ -9,7 +9,7 @@ import warnings
 import numpy as np
 import torch
 
-from ._lib import KDIP_ENOTCONV, OpDesc, PmvScalars, check, lib, ptr, stream_ptr
+from ._lib import KDIP_ENOTCONV, GuidedCfg, OpDesc, PmvScalars, check, lib, ptr, stream_ptr
 
 OP_KIND = {"inpainting": 0, "gaussian_blur": 1, "motion_blur": 2, "super_resolution": 3}
 OT_KIND = {None: 0, "dct": 1, "dwt": 2}
@@ -157,6 +157,76 @@ class OperatorHandle:
         return v, norm
 
 
+GUIDE = {"uncond": 0, "I": 1, "pgdm": 2, "dps": 3, "diffpir": 4}
+
+
+class FusedGuidedEval:
+    """kdip_guided_eval: one C call (and, after two eager calls, one CUDA-graph replay) per guided model evaluation for the
+    closed-form branches.  The scalars of the evaluation live in a pinned host struct that the graph's memcpy node re-reads at every
+    replay, so ONE graph per (guidance, B) serves every sigma of the schedule."""
+
+    def __init__(self, engine, handle):
+        self.engine, self.handle = engine, handle
+        self._cfg_host = torch.zeros(ctypes.sizeof(GuidedCfg), dtype=torch.uint8).pin_memory()
+        self.cfg = GuidedCfg.from_address(self._cfg_host.data_ptr())
+        self._graphs = {}
+        import os
+        self._graphs_on = os.environ.get("KDIP_CUDA_GRAPH", "1") != "0"
+
+    def _ws(self, B):
+        n = ctypes.c_size_t()
+        check(lib.kdip_guided_eval_workspace_bytes(self.engine._h, self.handle._h, B, ctypes.byref(n)))
+        ws, _ = self.engine._workspace(B, at_least=n.value)
+        return ws, n.value
+
+    def _launch(self, x, y, hat, B, ws, nb):
+        check(lib.kdip_guided_eval(self.engine._h, self.handle._h, ctypes.byref(self.cfg), ptr(x), ptr(y), ptr(hat), B, ws, nb,
+                                   stream_ptr()))
+
+    def __call__(self, guidance, sigma, t_model, theta, zeta, sc_one, x, y):
+        """sc_one: PmvScalars for this sigma (uniform over the batch).  x [B,3,S,S], y: measurement -> hat_x0."""
+        c = self.cfg
+        c.guidance, c.sigma, c.t_model, c.theta, c.zeta, c.sc = GUIDE[guidance], float(sigma), float(t_model), float(theta), float(zeta), sc_one
+        x, y = _f32(x), _f32(y)
+        B = x.shape[0]
+        ws, nb = self._ws(B)
+        hat = torch.empty_like(x)
+        key = (guidance, B, tuple(y.shape), ws.value)
+        r = self._graphs.setdefault(key, {"calls": 0, "graph": None, "failed": False}) if self._graphs_on else None
+        if r is not None and not r["failed"]:
+            r["calls"] += 1
+            if r["calls"] > 2 and r["graph"] is None:
+                try:
+                    r["x"], r["y"], r["hat"] = torch.zeros_like(x), torch.zeros_like(y), torch.zeros_like(x)
+                    cur, side = torch.cuda.current_stream(), torch.cuda.Stream()
+                    side.wait_stream(cur)
+                    with torch.cuda.stream(side):
+                        self._launch(r["x"], r["y"], r["hat"], B, ws, nb)       # settles every lazily built plan
+                    cur.wait_stream(side)
+                    torch.cuda.synchronize()
+                    g = torch.cuda.CUDAGraph()
+                    n0 = lib.kdip_launch_count()
+                    with torch.cuda.graph(g):
+                        self._launch(r["x"], r["y"], r["hat"], B, ws, nb)
+                    r["graph"], r["kernels"] = g, int(lib.kdip_launch_count() - n0)
+                except Exception as e:                                          # noqa: BLE001 - eager launches stay functional
+                    warnings.warn(f"kdip: CUDA-graph capture of the fused guided evaluation failed ({e}); using eager launches")
+                    r["failed"], r["graph"] = True, None
+            if r["graph"] is not None:
+                r["x"].copy_(x)
+                r["y"].copy_(y)
+                r["graph"].replay()
+                lib.kdip_launch_count_add(r["kernels"])
+                hat.copy_(r["hat"])
+                self.engine._fwd_N = B
+                self.engine.forward_token += 1
+                return hat
+        self._launch(x, y, hat, B, ws, nb)
+        self.engine._fwd_N = B
+        self.engine.forward_token += 1
+        return hat
+
+
 _ortho_ws = {}
 
 
@@ -179,21 +249,27 @@ def ortho(ot, x, inverse=False, mul=None):
 
 # ---- p_mean_variance epilogue / guidance combine -----------------------------------------------------------------------
 
+def pmv_scalars_one(diffusion, t, c_in, dst=None):
+    """kdip_pmv_scalars at integer timestep t from the float64 schedule (gaussian_diffusion.py:895-908: float64 -> fp32 at use)."""
+    e = PmvScalars() if dst is None else dst
+    tb = int(t)
+    e.c_in = float(np.float32(c_in))
+    e.recip = float(np.float32(diffusion.sqrt_recip_alphas_cumprod[tb]))
+    e.recipm1 = float(np.float32(diffusion.sqrt_recipm1_alphas_cumprod[tb]))
+    e.min_log = float(np.float32(diffusion.posterior_log_variance_clipped[tb]))
+    e.max_log = float(np.float32(np.log(diffusion.betas[tb])))
+    e.post_var = float(np.float32(diffusion.posterior_variance[tb]))
+    c1 = np.float32(diffusion.posterior_mean_coef1[tb])
+    e.coef1_sq = float(c1 * c1)
+    return e
+
+
 def pmv_scalars(diffusion, t, c_in, device):
-    """Per-image scalar table for the epilogue kernels from the float64 schedule at integer t
-    (gaussian_diffusion.py:895-908: numpy float64 -> fp32 at use).  t: list[int], c_in: list[float]."""
+    """Per-image scalar table for the epilogue kernels.  t: list[int], c_in: list[float]."""
     B = len(t)
     arr = (PmvScalars * B)()
     for b in range(B):
-        tb = int(t[b])
-        arr[b].c_in = float(np.float32(c_in[b]))
-        arr[b].recip = float(np.float32(diffusion.sqrt_recip_alphas_cumprod[tb]))
-        arr[b].recipm1 = float(np.float32(diffusion.sqrt_recipm1_alphas_cumprod[tb]))
-        arr[b].min_log = float(np.float32(diffusion.posterior_log_variance_clipped[tb]))
-        arr[b].max_log = float(np.float32(np.log(diffusion.betas[tb])))
-        arr[b].post_var = float(np.float32(diffusion.posterior_variance[tb]))
-        c1 = np.float32(diffusion.posterior_mean_coef1[tb])
-        arr[b].coef1_sq = float(c1 * c1)
+        pmv_scalars_one(diffusion, t[b], c_in[b], arr[b])
     host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
     return host.to(device, non_blocking=False)
 

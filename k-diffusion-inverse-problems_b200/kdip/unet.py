@@ -58,6 +58,7 @@ class UNetEngine:
         self._h = h
         self._ws = None
         self._ws_N = 0
+        self._ws_need = 0
         self._fwd_N = 0
         self.forward_token = 0   # bumped by every forward: the VJP is only valid for the latest one
         # CUDA-graph replay of the fixed launch lists (about 140 launches forward, 190 backward): after two eager calls per
@@ -78,13 +79,19 @@ class UNetEngine:
         check(lib.kdip_unet_workspace_bytes(self._h, N, ctypes.byref(b)))
         return b.value
 
-    def _workspace(self, N):
-        if self._ws is None or self._ws_N != N:
+    def _workspace(self, N, at_least=0):
+        """(aligned pointer, bytes the UNet plan is keyed on).  The buffer may be larger than the UNet's own need: the fused
+        guided evaluation (kdip.ops.FusedGuidedEval) places the UNet workspace first and its operator / guidance scratch behind it,
+        so both paths run the SAME launch plan (the library re-plans whenever (N, pointer, size) changes)."""
+        if self._ws is None or self._ws_N != N or self._ws.numel() - 256 < at_least:
+            need = self.workspace_bytes(N)
+            keep = max(need, at_least, (self._ws.numel() - 256) if (self._ws is not None and self._ws_N == N) else 0)
             self._ws = None
-            self._ws = torch.empty(self.workspace_bytes(N) + 256, dtype=torch.uint8, device=self.device)
-            self._ws_N = N
+            self._ws = torch.empty(keep + 256, dtype=torch.uint8, device=self.device)
+            self._ws_N, self._ws_need = N, need
+            self._replays.clear()          # captured graphs hold the old pointer
         off = (-self._ws.data_ptr()) % 256
-        return ctypes.c_void_p(self._ws.data_ptr() + off), self._ws.numel() - 256
+        return ctypes.c_void_p(self._ws.data_ptr() + off), self._ws_need
 
     def _replay(self, key, statics_fn, launch_fn):
         """Returns the (graph, static buffers) for `key` once two eager calls have happened, else None."""
