@@ -332,6 +332,7 @@ def guidance_roofline(cfg, operator, dev, B, pk):
     timeit("heun_step", 5, lambda: ops.heun_step(x, v, x0, grad, 1.2, -0.2))
     h = operator.handle
     y = h.forward(x0, None)
+    y = y + 0.05 * torch.randn(y.shape, generator=g).to(dev)        # a noisy measurement: y - A x0 != 0, the solvers have work to do
     if operator.name in ("gaussian_blur", "motion_blur"):
         timeit("A x (blur, spectral)", 2, lambda: h.forward(x0, None))
         timeit("A^T y (blur, spectral)", 2, lambda: h.transpose(y))

@@ -341,9 +341,10 @@ int kdip_unet_feature(kdip_unet* u, int N, float* feat, kdip_stream_t s);
  * (condition/condition.py:83-174) over ConditionOpenAIDenoiser.uncond_pred (:231-274) for every branch with a closed-form
  * mat solver: hat_x0 = clip(x0 + coef * J^T v, -1, 1).  One call enqueues UNet forward, p_mean_variance epilogue, mat solver
  * (or the DPS residual gradient), VJP seed, UNet input-VJP and the combine on `s` out of the caller's workspace: no allocation,
- * no synchronisation, capturable as ONE CUDA graph per (guidance, B).  `cfg` is copied to the device with cudaMemcpyAsync (under
- * capture a memcpy node: keep it in pinned host memory, update it and replay for the next sigma).  sigma is uniform over the
- * batch, as inside a sampler call.  The per-pixel covariance + CG branch (sigma < mle_sigma_thres with Convert / TMPD / DWT-Var)
+ * no synchronisation.  kdip_guided_eval = kdip_guided_eval_set (the scalars of `cfg` travel BY VALUE as kernel arguments into
+ * per-image device arrays of the workspace; the struct is not read after the call returns) + kdip_guided_eval_run (device-resident
+ * data only: capture it ONCE as a CUDA graph per (guidance, B), then per evaluation: _set eagerly, replay).  sigma is uniform over
+ * the batch, as inside a sampler call.  The per-pixel covariance + CG branch (sigma < mle_sigma_thres with Convert / TMPD / DWT-Var)
  * is NOT covered: it polls convergence on the host - use kdip_unet_* + kdip_mat_cg + kdip_guidance_combine.
  * ------------------------------------------------------------------------------------------------------------ */
 #define KDIP_GUIDE_UNCOND 0  /* hat_x0 = x0_mean                                                  condition.py:104-106 */
@@ -363,6 +364,9 @@ int kdip_guided_eval_workspace_bytes(kdip_unet* u, const kdip_op* op, int B, siz
 /* x [B,3,S,S] (unscaled x_t), y: the measurement (operator.forward's shape) -> hat_x0 [B,3,S,S]. */
 int kdip_guided_eval(kdip_unet* u, kdip_op* op, const kdip_guided_cfg* cfg, const float* x, const float* y, float* hat_x0, int B,
                      void* ws, size_t ws_bytes, kdip_stream_t s);
+int kdip_guided_eval_set(kdip_unet* u, const kdip_op* op, const kdip_guided_cfg* cfg, int B, void* ws, size_t ws_bytes, kdip_stream_t s);
+int kdip_guided_eval_run(kdip_unet* u, kdip_op* op, int guidance, const float* x, const float* y, float* hat_x0, int B, void* ws,
+                         size_t ws_bytes, kdip_stream_t s);
 
 /* ------------------------------------------------------------------------------------------------------------
  * UNet building blocks, exported for per-layer parity tests (tests/test_layers_gpu.py).  Activations are bf16 NHWC.

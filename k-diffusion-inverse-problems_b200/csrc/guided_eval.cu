@@ -2,10 +2,13 @@
 // ConditionOpenAIDenoiser.uncond_pred, :231-274) for the branches that need no iterative solver:
 //     UNet forward -> p_mean_variance epilogue -> mat (closed form, scalar x0 variance) or DPS residual gradient
 //     -> clamp / scaling VJP seed -> UNet input-VJP -> hat_x0 = clip(x0 + coef (c_in g + direct), -1, 1)
-// Everything is enqueued on the caller's stream from the caller's workspace: no allocation, no synchronisation, so the whole
-// evaluation can be captured into a single CUDA graph per (configuration, batch).  The per-evaluation scalars travel in a small
-// host struct that is copied to the device with cudaMemcpyAsync: under capture that is a memcpy NODE, i.e. a replay re-reads the
-// (pinned) host struct - update it, replay, and the same graph serves every sigma of the schedule.
+// Everything is enqueued on the caller's stream from the caller's workspace: no allocation, no synchronisation.  The call has two
+// halves, also exported on their own: kdip_guided_eval_set broadcasts the evaluation's scalars (passed BY VALUE as kernel
+// arguments - no host memory is read after the call returns) into per-image device arrays of the workspace, and
+// kdip_guided_eval_run does everything else from device-resident data only, so _run can be captured ONCE into a CUDA graph per
+// (guidance, batch) and replayed for every sigma of the schedule after an eager _set.  (A first version copied a pinned host
+// struct inside the graph; a replay then reads the struct when the GPU gets there, by which time the host may already have
+// written the next evaluation's scalars - measured as 2-18 % trajectory errors as soon as the host ran ahead.)
 // The per-pixel-covariance / CG branch (condition.py:325-346,359-384,412-437) polls convergence on the host and stays with the
 // individually exported pieces (kdip_mat_cg etc.), which is also what user-registered operators / mat solvers use.
 #include "kdip_common.cuh"
@@ -61,11 +64,11 @@ static int plan(kdip_unet* u, const kdip_op* op, int B, void* base, size_t* tota
 }
 
 // broadcast the evaluation's scalars (uniform over the batch inside a sampler call) into the per-image device arrays
-__global__ void ge_fill_kernel(const kdip_guided_cfg* __restrict__ cfg, kdip_pmv_scalars* __restrict__ sc, float* __restrict__ c_in,
-                               float* __restrict__ t, float* __restrict__ theta, float* __restrict__ coef, int B) {
+__global__ void ge_fill_kernel(const kdip_guided_cfg c, kdip_guided_cfg* __restrict__ cfg_dev, kdip_pmv_scalars* __restrict__ sc,
+                               float* __restrict__ c_in, float* __restrict__ t, float* __restrict__ theta, float* __restrict__ coef, int B) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
-  const kdip_guided_cfg c = *cfg;
+  if (b == 0) *cfg_dev = c;
   sc[b] = c.sc;
   c_in[b] = c.sc.c_in;
   t[b] = c.t_model;
@@ -93,23 +96,38 @@ extern "C" int kdip_guided_eval_workspace_bytes(kdip_unet* u, const kdip_op* op,
   return plan(u, op, B, nullptr, bytes, &w);
 }
 
-extern "C" int kdip_guided_eval(kdip_unet* u, kdip_op* op, const kdip_guided_cfg* cfg, const float* x, const float* y, float* hat_x0,
-                                int B, void* ws, size_t ws_bytes, kdip_stream_t stream) {
-  KDIP_REQUIRE(u && op && cfg && x && y && hat_x0 && B > 0, KDIP_EINVAL, "guided_eval: bad argument");
-  KDIP_REQUIRE(cfg->guidance >= KDIP_GUIDE_UNCOND && cfg->guidance <= KDIP_GUIDE_DIFFPIR, KDIP_EINVAL, "guided_eval: unknown guidance %d",
-               cfg->guidance);
+static int get_ws(kdip_unet* u, const kdip_op* op, int B, void* ws, size_t ws_bytes, GeWs* w) {
   KDIP_REQUIRE(ws != nullptr && ((uintptr_t)ws % 256) == 0, KDIP_EALIGN, "guided_eval: workspace must be 256-byte aligned");
-  GeWs w;
   size_t need = 0;
-  int rc = plan(u, op, B, ws, &need, &w);
+  int rc = plan(u, op, B, ws, &need, w);
   if (rc) return rc;
   KDIP_REQUIRE(need <= ws_bytes, KDIP_ENOMEM, "guided_eval: workspace too small: need %zu bytes, got %zu", need, ws_bytes);
+  return KDIP_OK;
+}
+
+extern "C" int kdip_guided_eval_set(kdip_unet* u, const kdip_op* op, const kdip_guided_cfg* cfg, int B, void* ws, size_t ws_bytes,
+                                    kdip_stream_t stream) {
+  KDIP_REQUIRE(u && op && cfg && B > 0, KDIP_EINVAL, "guided_eval_set: bad argument");
+  KDIP_REQUIRE(cfg->guidance >= KDIP_GUIDE_UNCOND && cfg->guidance <= KDIP_GUIDE_DIFFPIR, KDIP_EINVAL, "guided_eval: unknown guidance %d",
+               cfg->guidance);
+  GeWs w;
+  int rc = get_ws(u, op, B, ws, ws_bytes, &w);
+  if (rc) return rc;
+  ge_fill_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*cfg, w.cfg, w.sc, w.c_in, w.t, w.theta, w.coef, B);
+  KDIP_LAUNCH_CHECK();
+  return KDIP_OK;
+}
+
+extern "C" int kdip_guided_eval_run(kdip_unet* u, kdip_op* op, int guidance, const float* x, const float* y, float* hat_x0, int B,
+                                    void* ws, size_t ws_bytes, kdip_stream_t stream) {
+  KDIP_REQUIRE(u && op && x && y && hat_x0 && B > 0, KDIP_EINVAL, "guided_eval_run: bad argument");
+  KDIP_REQUIRE(guidance >= KDIP_GUIDE_UNCOND && guidance <= KDIP_GUIDE_DIFFPIR, KDIP_EINVAL, "guided_eval: unknown guidance %d", guidance);
+  GeWs w;
+  int rc = get_ws(u, op, B, ws, ws_bytes, &w);
+  if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const int S = kdip_op_side(op), HW = S * S, CHW = 3 * HW;
-  const int g = cfg->guidance;
-  KDIP_CUDA(cudaMemcpyAsync(w.cfg, cfg, sizeof(kdip_guided_cfg), cudaMemcpyHostToDevice, st));
-  ge_fill_kernel<<<(B + 127) / 128, 128, 0, st>>>(w.cfg, w.sc, w.c_in, w.t, w.theta, w.coef, B);
-  KDIP_LAUNCH_CHECK();
+  const int g = guidance;
   rc = kdip_unet_forward(u, x, w.c_in, w.t, B, w.out6, nullptr, w.unet_ws, w.unet_bytes, stream);
   if (rc) return rc;
   rc = kdip_pmv_epilogue(w.out6, x, w.sc, w.x0, nullptr, 0, B, HW, stream);
@@ -130,4 +148,11 @@ extern "C" int kdip_guided_eval(kdip_unet* u, kdip_op* op, const kdip_guided_cfg
   rc = kdip_unet_vjp(u, w.seed, B, w.grad, w.unet_ws, w.unet_bytes, stream);
   if (rc) return rc;
   return kdip_guidance_combine(w.x0, w.grad, w.direct, w.coef, w.c_in, hat_x0, B, CHW, stream);
+}
+
+extern "C" int kdip_guided_eval(kdip_unet* u, kdip_op* op, const kdip_guided_cfg* cfg, const float* x, const float* y, float* hat_x0,
+                                int B, void* ws, size_t ws_bytes, kdip_stream_t stream) {
+  int rc = kdip_guided_eval_set(u, op, cfg, B, ws, ws_bytes, stream);
+  if (rc) return rc;
+  return kdip_guided_eval_run(u, op, cfg->guidance, x, y, hat_x0, B, ws, ws_bytes, stream);
 }

@@ -161,14 +161,13 @@ GUIDE = {"uncond": 0, "I": 1, "pgdm": 2, "dps": 3, "diffpir": 4}
 
 
 class FusedGuidedEval:
-    """kdip_guided_eval: one C call (and, after two eager calls, one CUDA-graph replay) per guided model evaluation for the
-    closed-form branches.  The scalars of the evaluation live in a pinned host struct that the graph's memcpy node re-reads at every
-    replay, so ONE graph per (guidance, B) serves every sigma of the schedule."""
+    """kdip_guided_eval: one library call per guided model evaluation for the closed-form branches - and, after two eager calls,
+    kdip_guided_eval_set (a one-CTA kernel that takes the evaluation's scalars by value) + ONE CUDA-graph replay of
+    kdip_guided_eval_run, the same graph for every sigma of the schedule."""
 
     def __init__(self, engine, handle):
         self.engine, self.handle = engine, handle
-        self._cfg_host = torch.zeros(ctypes.sizeof(GuidedCfg), dtype=torch.uint8).pin_memory()
-        self.cfg = GuidedCfg.from_address(self._cfg_host.data_ptr())
+        self.cfg = GuidedCfg()
         self._graphs = {}
         import os
         self._graphs_on = os.environ.get("KDIP_CUDA_GRAPH", "1") != "0"
@@ -179,9 +178,9 @@ class FusedGuidedEval:
         ws, _ = self.engine._workspace(B, at_least=n.value)
         return ws, n.value
 
-    def _launch(self, x, y, hat, B, ws, nb):
-        check(lib.kdip_guided_eval(self.engine._h, self.handle._h, ctypes.byref(self.cfg), ptr(x), ptr(y), ptr(hat), B, ws, nb,
-                                   stream_ptr()))
+    def _run(self, x, y, hat, B, ws, nb):
+        check(lib.kdip_guided_eval_run(self.engine._h, self.handle._h, int(self.cfg.guidance), ptr(x), ptr(y), ptr(hat), B, ws, nb,
+                                       stream_ptr()))
 
     def __call__(self, guidance, sigma, t_model, theta, zeta, sc_one, x, y):
         """sc_one: PmvScalars for this sigma (uniform over the batch).  x [B,3,S,S], y: measurement -> hat_x0."""
@@ -191,6 +190,7 @@ class FusedGuidedEval:
         B = x.shape[0]
         ws, nb = self._ws(B)
         hat = torch.empty_like(x)
+        check(lib.kdip_guided_eval_set(self.engine._h, self.handle._h, ctypes.byref(c), B, ws, nb, stream_ptr()))
         key = (guidance, B, tuple(y.shape), ws.value)
         r = self._graphs.setdefault(key, {"calls": 0, "graph": None, "failed": False}) if self._graphs_on else None
         if r is not None and not r["failed"]:
@@ -201,13 +201,13 @@ class FusedGuidedEval:
                     cur, side = torch.cuda.current_stream(), torch.cuda.Stream()
                     side.wait_stream(cur)
                     with torch.cuda.stream(side):
-                        self._launch(r["x"], r["y"], r["hat"], B, ws, nb)       # settles every lazily built plan
+                        self._run(r["x"], r["y"], r["hat"], B, ws, nb)       # settles every lazily built plan
                     cur.wait_stream(side)
                     torch.cuda.synchronize()
                     g = torch.cuda.CUDAGraph()
                     n0 = lib.kdip_launch_count()
                     with torch.cuda.graph(g):
-                        self._launch(r["x"], r["y"], r["hat"], B, ws, nb)
+                        self._run(r["x"], r["y"], r["hat"], B, ws, nb)
                     r["graph"], r["kernels"] = g, int(lib.kdip_launch_count() - n0)
                 except Exception as e:                                          # noqa: BLE001 - eager launches stay functional
                     warnings.warn(f"kdip: CUDA-graph capture of the fused guided evaluation failed ({e}); using eager launches")
@@ -221,7 +221,7 @@ class FusedGuidedEval:
                 self.engine._fwd_N = B
                 self.engine.forward_token += 1
                 return hat
-        self._launch(x, y, hat, B, ws, nb)
+        self._run(x, y, hat, B, ws, nb)
         self.engine._fwd_N = B
         self.engine.forward_token += 1
         return hat

@@ -159,12 +159,13 @@ def test_sampler_trajectory(run, precision, tiny_models, golden_small, golden_tr
     print(f"trajectory {tag} [{precision}]: free-run max {e_max:.3e} l2 {e_l2:.3e}; per step l2 {['%.2e' % v for v in steps]}")
     assert e_l2 <= TRAJ_FREE[0 if precision == "fp32" else 1]
     for i, v in enumerate(steps):
-        # the parity claim: one sampler step from the reference's state.  fp32 engine: the tolerance; bf16 engine: the same two
-        # classes as the evaluations, by the sigma the step's model evaluation runs at
+        # the parity claim: one sampler step from the reference's state.  fp32 engine: the tolerance.  bf16 engine: the relative
+        # L2 floor for steps evaluated at sigma <= 0.5, the sanity bound above (x_{i+1} = x_i + (x_i - hat_x0) dt / sigma carries the
+        # evaluation's error with weight |dt| / sigma ~ 0.8, and inpainting / PiGDM at sigma = 1.3 already moves hat_x0 by 0.1)
         if precision == "fp32":
             assert v <= TOL_FP32, (tag, i, v)
         else:
-            assert v <= (BF16_FLOOR[0] if float(sig[i]) <= 1.5 else BF16_ILL_L2), (tag, i, v)
+            assert v <= (BF16_FLOOR[0] if float(sig[i]) <= 0.5 else BF16_ILL_L2), (tag, i, v)
 
 
 @pytest.mark.parametrize("sampler", ["euler", "heun"])
@@ -408,18 +409,26 @@ def test_fused_guided_eval_equals_composed_path(case, tiny_models, monkeypatch, 
         return ConditionOpenAIDenoiser(inner_model=model, diffusion=diffusion, x0_cov_type=cov, recon_mse=recon_mse(), operator=op,
                                        measurement=measurement(op, opname, batch=B), guidance=guidance, device="cuda",
                                        mle_sigma_thres=0.2, **extra).eval()
-    sigmas = [10.0, 3.0, 1.0, 0.5, 0.3]            # all above the MLE threshold: the closed-form branch of every case
+    sigmas = [10.0, 3.0, 1.0, 0.5, 0.3, 7.0, 0.25, 2.0]   # all above the MLE threshold: the closed-form branch of every case
     xs = [I.xt(64, s, seed=40 + i, batch=B).cuda() for i, s in enumerate(sigmas)]
+    sg = []
+    for s_ in sigmas:                              # as the samplers pass it: a device tensor carrying its host value (no read-back)
+        t = torch.full((B,), s_).cuda()
+        t._kdip_host = s_
+        sg.append(t)
     monkeypatch.setenv("KDIP_FUSED_EVAL", "1")
     cm = build()
-    fused = [cm(x, torch.full((B,), s).cuda()).clone() for x, s in zip(xs, sigmas)]
+    torch.cuda.synchronize()
+    # back to back, nothing in between synchronises: the host runs evaluations ahead of the GPU, which is when a scalar that a
+    # replay reads late (instead of at launch) would be the NEXT evaluation's
+    fused = [cm(x, t) for x, t in zip(xs, sg)]
     assert getattr(cm, "_fused", None) is not None, "the fused path was not taken"
     assert any(r.get("graph") is not None for r in cm._fused._graphs.values()), "the fused evaluation was not captured into a CUDA graph"
     monkeypatch.setenv("KDIP_FUSED_EVAL", "0")
     cm0 = build()
     worst = 0.0
-    for f, x, s in zip(fused, xs, sigmas):
-        ref = cm0(x, torch.full((B,), s).cuda())
+    for f, x, t in zip(fused, xs, sg):
+        ref = cm0(x, t)
         worst = max(worst, (f - ref).abs().max().item())
     assert getattr(cm0, "_fused", None) is None
     parity_log(f"fused_vs_composed.{opname}.{guidance}.{cov}[fp32]", max_abs_diff=worst)
