@@ -250,6 +250,14 @@ typedef struct {
   int gn_silu;          /* 1: act = SiLU, 0: identity */
   const float* gn_ab;   /* fp32 [N,Cout,2] folded affine (A, B) of the forward pass */
   float* gn_red;        /* fp32 [N,Cout,2], zeroed by the caller; NULL to skip */
+  /* Optional fused GroupNorm apply on the operand path (forward of nn.py:17-19 + SiLU in front of the conv, unet.py:237-257 in_layers /
+   * out_layers): segment s is consumed as act(A x + B) with (A, B) = in_ab[s][(n * in_ab_C + c) * 2 + {0,1}] for channel c of the
+   * segment (in_ab[s] already points at the segment's first channel inside a [N, in_ab_C, 2] table; NULL = segment read as is).  The
+   * values are rounded to bf16 exactly as kdip_gn_apply stores them and the conv pads the NORMALISED tensor with zeros.  Needs the
+   * row-tile ("halo") pipeline: 3x3 first segment, W a multiple of 128, even H, bf16 NHWC output with Cout a multiple of 64. */
+  const float* in_ab[3];
+  int in_ab_C;
+  int in_silu;          /* 1: act = SiLU, 0: identity */
 } kdip_conv_desc;
 
 typedef struct kdip_conv_plan kdip_conv_plan; /* encoded TMA descriptors + launch geometry */

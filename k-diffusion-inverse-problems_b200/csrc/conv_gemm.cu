@@ -30,6 +30,7 @@ static constexpr int kBlockM = 128;
 static constexpr int kBlockK = 64;                      // bf16 elements = 128 bytes = one swizzle row
 static constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KiB
 static constexpr int kThreads = 384;                    // 4 control warps + 8 epilogue warps
+static constexpr int kXfThreads = 640;                  // + 8 operand-transform warps (fused GroupNorm apply, halo pipeline only)
 static constexpr int kEpiThreads = 256;
 static constexpr int kSlabBytes = kBlockM * 128;        // one 64-channel bf16 slab of the output tile: 16 KiB
 static constexpr int kStagingBytes = 2 * kSlabBytes;    // 128 channels at a time
@@ -56,7 +57,8 @@ struct ConvParams {
   int halo;             // 1: halo pipeline (see kHaloPix)
   int halo_bo;          // 1: descriptors carry the matrix base offset (probe only; wrong on B200, see conv_plan_build)
   int ws;               // 1: the two tiles of a work item share the weight operand through the tensor core's collector (tcgen05.mma.ws)
-  int dbg;              // timing experiments only (KDIP_CONV_DBG): 1 = no operand loads / waits, 2 = epilogue releases TMEM without reading or storing
+  int dbg;              // timing experiments only (KDIP_CONV_DBG): 1 = no operand loads / waits, 2 = epilogue releases TMEM without reading or storing,
+                        // 4 = operand-transform warps only hand the rows over, 8 = they copy the rows through registers without the math
   uint32_t res_slab_bytes;   // bytes TMA lands per 64-channel slab of the skip / GroupNorm-source tile
   int b_rows;           // weight rows each CTA loads per k-block: BN (single) or BN/2 (pair)
   int total_work;       // persistent-loop trip count: tiles (single) or pair tiles (pair)
@@ -81,6 +83,9 @@ struct ConvParams {
   const float* gn_ab;
   float* gn_red;
   int gn_C0, gn_silu, gn_two;
+  // fused GroupNorm apply on the operand path (kdip_conv_desc.in_ab): segment s is consumed as act(A x + B)
+  const float* xf_ab[3];
+  int xf_C, xf_silu;
 };
 
 struct TileCoord {
@@ -124,8 +129,17 @@ __device__ __forceinline__ int work_to_tile(const ConvParams& p, int work, int r
   return m * p.n_tiles + nt;
 }
 
-template <bool kPair, bool kHalo>
-__global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvParams p) {
+// register budgets of the 640-thread variant (setmaxnreg per warpgroup): the CTA starts with 640 x 96 registers;
+// control warps 56, two epilogue warpgroups 144, two transform warpgroups 64: (56 + 2 x 144 + 2 x 64) x 128 = 60416 <= 61440
+__device__ __forceinline__ void setmaxnreg_dec_56() { asm volatile("setmaxnreg.dec.sync.aligned.u32 56;" ::: "memory"); }
+__device__ __forceinline__ void setmaxnreg_dec_64() { asm volatile("setmaxnreg.dec.sync.aligned.u32 64;" ::: "memory"); }
+__device__ __forceinline__ void setmaxnreg_inc_144() { asm volatile("setmaxnreg.inc.sync.aligned.u32 144;" ::: "memory"); }
+
+// kXf (halo pipeline only): eight more warps (two warpgroups taking alternate rows) apply the GroupNorm affine + SiLU of the conv's input (nn.py:17-19, unet.py:237-257) to the
+// activation rows IN shared memory, between the TMA landing and the MMAs - the normalised tensor never exists in HBM.
+template <bool kPair, bool kHalo, bool kXf>
+__global__ void __launch_bounds__(kXf ? kXfThreads : kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvParams p) {
+  static_assert(!kXf || kHalo, "the operand transform lives in the halo pipeline");
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment required by the 128B swizzle atoms (TMA destination and UMMA descriptors)
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -153,6 +167,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_empty_bar + 1);
   uint64_t* a_full_bar = res_empty_bar + 2;            // halo mode: activation-row slots
   uint64_t* a_empty_bar = a_full_bar + kHaloSlots;
+  uint64_t* a_ready_bar = a_empty_bar + kHaloSlots;    // kXf: rows transformed (4 warps per CTA arrive; on the leader for pairs)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -181,8 +196,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     mbar_init(res_empty_bar, kEpiThreads);
     if (kHalo) {
       for (int s = 0; s < kHaloSlots; ++s) {
-        mbar_init(&a_full_bar[s], kPair ? 2 : 1);   // pair: one arrive.expect_tx per CTA, both on the leader's barrier
+        // pair: one arrive.expect_tx per CTA, both on the leader's barrier; kXf: every CTA's rows land on its own barrier
+        mbar_init(&a_full_bar[s], (kPair && !kXf) ? 2 : 1);
         mbar_init(&a_empty_bar[s], 1);
+        if (kXf) mbar_init(&a_ready_bar[s], kPair ? 8 : 4);
       }
     }
     fence_barrier_init();
@@ -196,10 +213,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   if (kPair) cluster_sync_all();   // the peer's barriers must be initialised before any remote arrive / multicast commit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-
   int kblocks_total = 0;
   for (int s = 0; s < p.nseg; ++s) kblocks_total += p.seg_taps[s] * p.seg_chunks[s];
 
+  // kXf: every warpgroup sets its register budget at the top of its own role branch (ptxas allocates per region; a budget set in
+  // code that all roles share afterwards would cap every role at the smallest one)
+  if (warp < 4) {
+  if (kXf) setmaxnreg_dec_56();
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (kHalo) {
@@ -216,7 +236,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
               for (int r = 0; r < nrows; ++r) {
                 mbar_wait(&a_empty_bar[slot], ph ^ 1);
                 if (!elect_one_sync()) {
-                } else if (kPair) {
+                } else if (kPair && !kXf) {
                   const uint32_t fb = leader_addr(&a_full_bar[slot]);
                   mbar_arrive_expect_tx_cluster(fb, (uint32_t)kHaloRowBytes);
                   tma_load_4d_2sm(smem + slot * kHaloSlot, &p.mapA[s], fb, ch * kBlockK, t.x0 - 1, ybase + r, t.n0);
@@ -297,8 +317,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
               for (int dyi = 0; dyi < ndy; ++dyi) {
                 // tile 0 (row y0) reads slot row dyi, tile 1 (row y0+1) reads slot row dyi+1
                 if (!(p.dbg & 1)) {
-                  if (dyi == 0) mbar_wait(&a_full_bar[rs[0]], rp[0]);
-                  mbar_wait(&a_full_bar[rs[dyi + 1]], rp[dyi + 1]);
+                  uint64_t* a_rdy = kXf ? a_ready_bar : a_full_bar;
+                  if (dyi == 0) mbar_wait(&a_rdy[rs[0]], rp[0]);
+                  mbar_wait(&a_rdy[rs[dyi + 1]], rp[dyi + 1]);
                 }
                 tc_fence_after();
                 const int ndx = k3 ? 3 : 1;
@@ -450,7 +471,96 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         }
       }
     }
-  } else if (warp >= 4 && p.tma_epilogue) {
+  }
+  } else if (kXf && warp >= 12) {
+    setmaxnreg_dec_64();
+    // ===================== operand transform: act(A x + B) on the landed rows, in place =====================
+    // Thread tt owns the logical 16-byte chunk j = tt & 7 (channels 8j .. 8j+7 of the 64-channel block) of the pixels (tt >> 3) + 16 i;
+    // the 128B swizzle keeps it in physical chunk j ^ (pixel & 7), the same for all of them.  Pixels outside the image were
+    // zero-filled by TMA and stay zero: the conv pads the NORMALISED activation (unet.py:185,211).
+    if (!(p.dbg & 1)) {
+      const int tt = (threadIdx.x - 384) & 127, wg = (threadIdx.x - 384) >> 7;
+      const int j = tt & 7, pb = tt >> 3;
+      uint32_t rowctr = 0;
+      const uint32_t col = (uint32_t)((j ^ (pb & 7)) << 4);
+      int slot = 0;
+      uint32_t ph = 0;
+      for (int work = work0; work < p.total_work; work += work_stride) {
+        const TileCoord t = decode_tile(p, work_to_tile(p, work, rank, 0));
+        const bool edge_l = t.x0 == 0, edge_r = t.x0 + 128 >= p.W;
+        for (int s = 0; s < p.nseg; ++s) {
+          const int nrows = p.seg_taps[s] == 9 ? 4 : 2;
+          const int ybase = p.seg_taps[s] == 9 ? t.y0 - 1 : t.y0;
+          const float* abp = p.xf_ab[s];
+          for (int ch = 0; ch < p.seg_chunks[s]; ++ch) {
+            float A[8], B[8];
+            if (abp != nullptr) {
+              const float4* q = reinterpret_cast<const float4*>(abp + ((size_t)t.n0 * p.xf_C + ch * kBlockK + j * 8) * 2);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float4 v = __ldg(q + e);
+                A[2 * e] = v.x; B[2 * e] = v.y; A[2 * e + 1] = v.z; B[2 * e + 1] = v.w;
+              }
+              if (p.xf_silu) {   // silu(u) = h + h tanh(h), h = u / 2: halving (A, B) is exact, so h (and the result) keep silu_fast's bits
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { A[e] *= 0.5f; B[e] *= 0.5f; }
+              }
+            }
+            for (int r = 0; r < nrows; ++r, ++rowctr) {
+              if ((int)(rowctr & 1u) != wg) {      // the other warpgroup's row
+                if (++slot == kHaloSlots) { slot = 0; ph ^= 1; }
+                continue;
+              }
+              mbar_wait(&a_full_bar[slot], ph);
+              const int y = ybase + r;
+              if (abp != nullptr && y >= 0 && y < p.H && !(p.dbg & 4)) {
+                uint8_t* row = smem + slot * kHaloSlot + col;
+                auto xform = [&](uint4& u) {
+                  float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y), f2 = unpack_bf16(u.z), f3 = unpack_bf16(u.w);
+                  f0.x = fmaf(A[0], f0.x, B[0]); f0.y = fmaf(A[1], f0.y, B[1]); f1.x = fmaf(A[2], f1.x, B[2]); f1.y = fmaf(A[3], f1.y, B[3]);
+                  f2.x = fmaf(A[4], f2.x, B[4]); f2.y = fmaf(A[5], f2.y, B[5]); f3.x = fmaf(A[6], f3.x, B[6]); f3.y = fmaf(A[7], f3.y, B[7]);
+                  if (p.dbg & 8) return;
+                  if (p.xf_silu) {
+                    f0.x = fmaf(f0.x, fast_tanh(f0.x), f0.x); f0.y = fmaf(f0.y, fast_tanh(f0.y), f0.y);
+                    f1.x = fmaf(f1.x, fast_tanh(f1.x), f1.x); f1.y = fmaf(f1.y, fast_tanh(f1.y), f1.y);
+                    f2.x = fmaf(f2.x, fast_tanh(f2.x), f2.x); f2.y = fmaf(f2.y, fast_tanh(f2.y), f2.y);
+                    f3.x = fmaf(f3.x, fast_tanh(f3.x), f3.x); f3.y = fmaf(f3.y, fast_tanh(f3.y), f3.y);
+                  }
+                  u.x = pack_bf16(f0.x, f0.y); u.y = pack_bf16(f1.x, f1.y); u.z = pack_bf16(f2.x, f2.y); u.w = pack_bf16(f3.x, f3.y);
+                };
+#pragma unroll
+                for (int i0 = 0; i0 < 8; i0 += 4) {
+                  uint4 v[4];
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) v[i] = *reinterpret_cast<const uint4*>(row + (pb + 16 * (i0 + i)) * 128);
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    const int px = pb + 16 * (i0 + i);
+                    if (!(edge_l && px == 0)) {       // pixel x0-1 outside the image
+                      xform(v[i]);
+                      *reinterpret_cast<uint4*>(row + px * 128) = v[i];
+                    }
+                  }
+                }
+                if (pb < 2 && !(edge_r && pb == 1)) {   // pixels 128 and 129 (= x0+128, outside the image on the right edge)
+                  uint4 v = *reinterpret_cast<const uint4*>(row + (pb + 128) * 128);
+                  xform(v);
+                  *reinterpret_cast<uint4*>(row + (pb + 128) * 128) = v;
+                }
+                fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's async-proxy reads
+              }
+              __syncwarp();
+              if (lane == 0) {
+                if (kPair) mbar_arrive_cluster(leader_addr(&a_ready_bar[slot])); else mbar_arrive(&a_ready_bar[slot]);
+              }
+              if (++slot == kHaloSlots) { slot = 0; ph ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp >= 4 && warp < 12 && (kXf || p.tma_epilogue)) {
+    if (kXf) setmaxnreg_inc_144();
     // ===================== epilogue (TMA store): 8 warps; warp (q, g) owns TMEM lanes [32q, 32q+32) x slab g =====================
     const int q = warp & 3;
     const int g = (warp - 4) >> 2;
@@ -624,7 +734,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       if (elect_one_sync()) tma_store_wait_all();
       __syncwarp();
     }
-  } else if (warp >= 4 && warp < 8) {
+  } else if (!kXf && warp >= 4 && warp < 8) {
     // ===================== legacy epilogue: 4 warps, warp q owns TMEM lanes [32q, 32q+32) =====================
     const int q = warp & 3;
     const int row = q * 32 + lane;
@@ -771,6 +881,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 struct ConvPlan {
   ConvParams params;
   int grid;
+  int xf;          // 512-thread variant with the operand-transform warps
   size_t smem_bytes;
 };
 
@@ -793,19 +904,21 @@ static int pick_bn(int cout_pad, int m_tiles) {
 static void set_smem_attr() {
   static bool attr_set = false;
   if (attr_set) return;
-  cudaFuncSetAttribute(conv_gemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  cudaFuncSetAttribute(conv_gemm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  cudaFuncSetAttribute(conv_gemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  cudaFuncSetAttribute(conv_gemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaFuncSetAttribute(conv_gemm_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaFuncSetAttribute(conv_gemm_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaFuncSetAttribute(conv_gemm_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaFuncSetAttribute(conv_gemm_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaFuncSetAttribute(conv_gemm_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaFuncSetAttribute(conv_gemm_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   attr_set = true;
 }
 
-static int max_active_pairs(size_t smem_bytes) {
+static int max_active_pairs(size_t smem_bytes, bool xf) {
   set_smem_attr();
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(2 * num_sms());
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(xf ? kXfThreads : kThreads);
   cfg.dynamicSmemBytes = smem_bytes;
   cudaLaunchAttribute attr;
   attr.id = cudaLaunchAttributeClusterDimension;
@@ -813,7 +926,9 @@ static int max_active_pairs(size_t smem_bytes) {
   cfg.attrs = &attr;
   cfg.numAttrs = 1;
   int n = 0;
-  if (cudaOccupancyMaxActiveClusters(&n, conv_gemm_kernel<true, false>, &cfg) != cudaSuccess) { cudaGetLastError(); return -1; }
+  const cudaError_t e = xf ? cudaOccupancyMaxActiveClusters(&n, conv_gemm_kernel<true, true, true>, &cfg)
+                           : cudaOccupancyMaxActiveClusters(&n, conv_gemm_kernel<true, false, false>, &cfg);
+  if (e != cudaSuccess) { cudaGetLastError(); return -1; }
   return n;
 }
 
@@ -833,6 +948,23 @@ bool conv_can_fuse_gn_reduce(const kdip_conv_desc* d) {
   tile_dims(d->H, d->W, &TW, &TH);
   if (TW <= 0 || kBlockM % TW != 0 || TH <= 0 || (kBlockM / TW) % TH != 0) return false;
   return d->W % TW == 0 && d->H % TH == 0;
+}
+
+// halo pipeline: a 3x3 first segment on an image at least 128 pixels wide, bf16 NHWC output in 64-channel slabs
+static bool conv_uses_halo(const kdip_conv_desc* d) {
+  if (!(d->seg[0].taps == 9 && d->W % 128 == 0 && d->H % 2 == 0 && d->out_mode == 0 && d->Cout == d->Cout_pad && d->Cout % 64 == 0 &&
+        d->res_mode != 2))
+    return false;
+  // KDIP_CONV_HALO=0 selects the 8x16-tile pipeline everywhere (A/B measurements)
+  if (getenv("KDIP_CONV_HALO") && atoi(getenv("KDIP_CONV_HALO")) == 0) return false;
+  if (const char* e = getenv("KDIP_CONV_TMAEPI")) { if (atoi(e) == 0) return false; }
+  return true;
+}
+// Can the GroupNorm apply (+SiLU) of this conv's input ride on its operand path (kdip_conv_desc.in_ab)?  Only the halo pipeline
+// has the transform warps; KDIP_FUSE_GNAPPLY=0 keeps the separate gn_apply pass everywhere (A/B measurements).
+bool conv_can_fuse_gn_apply(const kdip_conv_desc* d) {
+  if (getenv("KDIP_FUSE_GNAPPLY") && atoi(getenv("KDIP_FUSE_GNAPPLY")) == 0) return false;
+  return conv_uses_halo(d);
 }
 
 int conv_plan_build(const kdip_conv_desc* d, ConvPlan* plan) {
@@ -855,15 +987,24 @@ int conv_plan_build(const kdip_conv_desc* d, ConvPlan* plan) {
   KDIP_REQUIRE(d->chan_stats == nullptr || d->out_mode == 0, KDIP_EINVAL, "conv: chan_stats only with bf16 output");
 
   p.N = d->N; p.H = d->H; p.W = d->W;
-  // halo pipeline: a 3x3 first segment on an image at least 128 pixels wide, bf16 NHWC output in 64-channel slabs
-  p.halo = (d->seg[0].taps == 9 && d->W % 128 == 0 && d->H % 2 == 0 && d->out_mode == 0 && d->Cout == d->Cout_pad && d->Cout % 64 == 0 &&
-            d->res_mode != 2) ? 1 : 0;
+  p.halo = conv_uses_halo(d) ? 1 : 0;
   // Measured on B200 under sustained load (tools/time_unet.py 32 50), AFTER the issue loops became converged-warp + elect.sync:
   // 8x16 tiles 41.0 ms per UNet evaluation, halo pipeline 40.7 ms, halo pipeline as CTA pairs 38.1 ms.  (With the old lane-0 issue
   // loops, which paced every variant at ~1000 clk per k-block, the same A/B read 47.4 / 48.0 / 49.0 ms and the halo was opt-in.)
   // KDIP_CONV_HALO=0 selects the 8x16-tile pipeline everywhere.
-  if (getenv("KDIP_CONV_HALO") && atoi(getenv("KDIP_CONV_HALO")) == 0) p.halo = 0;
-  if (const char* e = getenv("KDIP_CONV_TMAEPI")) { if (atoi(e) == 0) p.halo = 0; }
+  bool xf = false;
+  for (int s = 0; s < d->nseg; ++s) {
+    p.xf_ab[s] = d->in_ab[s];
+    if (d->in_ab[s] != nullptr) xf = true;
+  }
+  p.xf_C = d->in_ab_C; p.xf_silu = d->in_silu;
+  if (xf) {
+    KDIP_REQUIRE(p.halo, KDIP_ESHAPE, "conv: the fused GroupNorm apply (in_ab) needs the halo pipeline: 3x3 first segment, W a multiple of 128, even H, bf16 NHWC output in 64-channel slabs");
+    KDIP_REQUIRE(d->in_ab_C > 0 && d->in_ab_C % 8 == 0, KDIP_EINVAL, "conv: in_ab_C=%d must be the (positive, multiple of 8) channel count of the (A, B) table", d->in_ab_C);
+    for (int s = 0; s < d->nseg; ++s)
+      KDIP_REQUIRE(((uintptr_t)d->in_ab[s] % 16) == 0, KDIP_EALIGN, "conv: in_ab[%d] must be 16B aligned", s);
+  }
+  plan->xf = xf ? 1 : 0;
   // Measured on B200 (tools/halo_probe.py): the 128B swizzle of tcgen05.mma operands is a function of the ABSOLUTE shared-memory
   // address, so a descriptor may start any number of 128-byte rows into a 1024-byte atom with base offset 0; setting the
   // matrix-base-offset field to the row phase gives wrong products.  KDIP_HALO_BASEOFF=1 re-enables it for that probe only.
@@ -1019,7 +1160,7 @@ int conv_plan_build(const kdip_conv_desc* d, ConvPlan* plan) {
   int sms = num_sms();
   if (p.pair) {
     // a persistent kernel must be fully co-resident: ask the driver how many CTA pairs fit at this shared-memory size
-    int clusters = max_active_pairs(plan->smem_bytes);
+    int clusters = max_active_pairs(plan->smem_bytes, xf);
     if (clusters <= 0 || clusters > sms / 2) clusters = sms / 2;
     if (getenv("KDIP_CONV_DEBUG")) fprintf(stderr, "[kdip conv] pair clusters co-resident: %d\n", clusters);
     plan->grid = 2 * (p.total_work < clusters ? p.total_work : clusters);
@@ -1035,7 +1176,7 @@ int conv_plan_launch(const ConvPlan* plan, cudaStream_t stream) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(plan->grid);
-    cfg.blockDim = dim3(kThreads);
+    cfg.blockDim = dim3(plan->xf ? kXfThreads : kThreads);
     cfg.dynamicSmemBytes = plan->smem_bytes;
     cfg.stream = stream;
     cudaLaunchAttribute attr;
@@ -1043,13 +1184,15 @@ int conv_plan_launch(const ConvPlan* plan, cudaStream_t stream) {
     attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
     cfg.attrs = &attr;
     cfg.numAttrs = 1;
-    if (plan->params.halo) KDIP_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<true, true>, plan->params));
-    else KDIP_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<true, false>, plan->params));
+    if (plan->xf) KDIP_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<true, true, true>, plan->params));
+    else if (plan->params.halo) KDIP_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<true, true, false>, plan->params));
+    else KDIP_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<true, false, false>, plan->params));
     count_launch();
     return KDIP_OK;
   }
-  if (plan->params.halo) conv_gemm_kernel<false, true><<<plan->grid, kThreads, plan->smem_bytes, stream>>>(plan->params);
-  else conv_gemm_kernel<false, false><<<plan->grid, kThreads, plan->smem_bytes, stream>>>(plan->params);
+  if (plan->xf) conv_gemm_kernel<false, true, true><<<plan->grid, kXfThreads, plan->smem_bytes, stream>>>(plan->params);
+  else if (plan->params.halo) conv_gemm_kernel<false, true, false><<<plan->grid, kThreads, plan->smem_bytes, stream>>>(plan->params);
+  else conv_gemm_kernel<false, false, false><<<plan->grid, kThreads, plan->smem_bytes, stream>>>(plan->params);
   KDIP_LAUNCH_CHECK();
   return KDIP_OK;
 }

@@ -42,6 +42,7 @@ struct ConvPlan;  // conv_gemm.cu
 int conv_plan_build(const kdip_conv_desc* d, ConvPlan* plan);
 int conv_plan_launch(const ConvPlan* plan, cudaStream_t stream);
 bool conv_can_fuse_gn_reduce(const kdip_conv_desc* d);
+bool conv_can_fuse_gn_apply(const kdip_conv_desc* d);
 ConvPlan* conv_plan_new();
 void conv_plan_free(ConvPlan* p);
 
@@ -56,6 +57,7 @@ struct DevBuf {
 struct ResWeights {
   const float *g1, *b1, *g2, *b2;       // GroupNorm affine
   bf16 *w1, *w1d, *w2, *w2d;            // conv weights, forward / dgrad
+  bf16 *w1s0, *w1s1;                    // conv1 forward weights split by source (concatenated input read as two K-segments)
   bf16 *ws0, *ws1, *wsd;                // 1x1 skip: forward split by source, dgrad (all input channels)
   const float *bias1, *bias2;           // bias2 already includes the skip conv's bias
   int film_off;                         // offset of (scale, shift) in the emb_proj table
@@ -327,6 +329,10 @@ extern "C" int kdip_unet_create(const kdip_unet_arch* arch, int n_tensors, const
       TRY(keep(p + ".out_layers.0.bias", co, &rw.b2));
       TRY(pack(p + ".in_layers.2.weight", co, ci, 0, ci, 9, 0, &rw.w1));
       TRY(pack(p + ".in_layers.2.weight", co, ci, 0, ci, 9, 1, &rw.w1d));
+      if (b.skip_ch > 0 && (ci - b.skip_ch) % 64 == 0 && b.skip_ch % 64 == 0) {
+        TRY(pack(p + ".in_layers.2.weight", co, ci, 0, ci - b.skip_ch, 9, 0, &rw.w1s0));
+        TRY(pack(p + ".in_layers.2.weight", co, ci, ci - b.skip_ch, b.skip_ch, 9, 0, &rw.w1s1));
+      }
       TRY(pack(p + ".out_layers.3.weight", co, co, 0, co, 9, 0, &rw.w2));
       TRY(pack(p + ".out_layers.3.weight", co, co, 0, co, 9, 1, &rw.w2d));
       TRY(keep(p + ".in_layers.2.bias", co, &rw.bias1));
@@ -621,19 +627,33 @@ static int build_launch_plan(kdip_unet* u, int N, void* ws, size_t ws_bytes, siz
         F.push_back([=](cudaStream_t s) {
           return launch_gn_finalize(s0.stats, s0.C, s1.stats, s1.C, n, P_in, w.g1, w.b1, nullptr, 0, 0, ab1, mr1, s);
         });
-        F.push_back([=](cudaStream_t s) { return launch_gn_apply(s0.p, s0.C, s1.p, s1.C, n, Hin, Hin, ab1, 1, rs, scrA, s, xpool); });
         kdip_conv_desc d1;
         memset(&d1, 0, sizeof(d1));
         d1.N = N; d1.H = Ho; d1.W = Ho; d1.Cout_pad = cout; d1.Cout = cout; d1.nseg = 1;
         d1.seg[0].act = scrA; d1.seg[0].C = cin; d1.seg[0].wgt = w.w1; d1.seg[0].taps = 9;
         d1.bias = w.bias1; d1.out = h1.p; d1.out_mode = 0; d1.out_scale = 1.f;
         if (fused_stats) d1.chan_stats = h1.stats;
+        // GroupNorm + SiLU of in_layers (unet.py:237-243) on the conv's operand path where the row-tile pipeline runs: the
+        // normalised tensor is never written; a concatenated input is two 3x3 K-segments over the raw sources
+        bool fuse1 = false;
+        if (rs == RS_NONE && (s1.C == 0 || (w.w1s0 != nullptr && w.w1s1 != nullptr))) {
+          kdip_conv_desc df = d1;
+          df.seg[0].act = s0.p; df.seg[0].C = s0.C; df.seg[0].wgt = s1.C > 0 ? w.w1s0 : w.w1;
+          df.in_ab[0] = ab1;
+          if (s1.C > 0) {
+            df.seg[1].act = s1.p; df.seg[1].C = s1.C; df.seg[1].wgt = w.w1s1; df.seg[1].taps = 9;
+            df.in_ab[1] = ab1 + (size_t)s0.C * 2;
+            df.nseg = 2;
+          }
+          df.in_ab_C = cin; df.in_silu = 1;
+          if (conv_can_fuse_gn_apply(&df)) { d1 = df; fuse1 = true; }
+        }
+        if (!fuse1) F.push_back([=](cudaStream_t s) { return launch_gn_apply(s0.p, s0.C, s1.p, s1.C, n, Hin, Hin, ab1, 1, rs, scrA, s, xpool); });
         add_conv_op(F, conv(d1));
         stats_op(F, h1);
         F.push_back([=](cudaStream_t s) {
           return launch_gn_finalize(h1.stats, cout, nullptr, 0, n, Po, w.g2, w.b2, film, R, w.film_off, ab2, mr2, s);
         });
-        F.push_back([=](cudaStream_t s) { return launch_gn_apply(h1.p, cout, nullptr, 0, n, Ho, Ho, ab2, 1, RS_NONE, scrB, s); });
         kdip_conv_desc d2;
         memset(&d2, 0, sizeof(d2));
         d2.N = N; d2.H = Ho; d2.W = Ho; d2.Cout_pad = cout; d2.Cout = cout;
@@ -649,6 +669,15 @@ static int build_launch_plan(kdip_unet* u, int N, void* ws, size_t ws_bytes, siz
         }
         d2.bias = w.bias2; d2.out = sr.out.p; d2.out_mode = 0; d2.out_scale = 1.f;
         if (fused_stats) d2.chan_stats = sr.out.stats;
+        // GroupNorm + FiLM + SiLU of out_layers (unet.py:244-254) on the operand path (the skip segments stay raw)
+        bool fuse2 = false;
+        {
+          kdip_conv_desc df = d2;
+          df.seg[0].act = h1.p;
+          df.in_ab[0] = ab2; df.in_ab_C = cout; df.in_silu = 1;
+          if (conv_can_fuse_gn_apply(&df)) { d2 = df; fuse2 = true; }
+        }
+        if (!fuse2) F.push_back([=](cudaStream_t s) { return launch_gn_apply(h1.p, cout, nullptr, 0, n, Ho, Ho, ab2, 1, RS_NONE, scrB, s); });
         add_conv_op(F, conv(d2));
       }
       stats_op(F, sr.out);

@@ -105,7 +105,8 @@ class ConvDesc(ctypes.Structure):
                 ("residual", ctypes.c_void_p), ("res_mode", ctypes.c_int), ("out", ctypes.c_void_p),
                 ("out_mode", ctypes.c_int), ("out_scale", ctypes.c_float), ("chan_stats", ctypes.c_void_p),
                 ("gn_x0", ctypes.c_void_p), ("gn_x1", ctypes.c_void_p), ("gn_C0", ctypes.c_int), ("gn_silu", ctypes.c_int),
-                ("gn_ab", ctypes.c_void_p), ("gn_red", ctypes.c_void_p)]
+                ("gn_ab", ctypes.c_void_p), ("gn_red", ctypes.c_void_p), ("in_ab", ctypes.c_void_p * 3), ("in_ab_C", ctypes.c_int),
+                ("in_silu", ctypes.c_int)]
 
 
 class UNetArch(ctypes.Structure):

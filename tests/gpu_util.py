@@ -39,8 +39,9 @@ def pack_weight(w, flip=False, ci_off=0, ci_sub=None):
     return dst, rp
 
 
-def run_conv(segs, N, H, W, cout, bias=None, residual=None, res_mode=0, out_mode=0, out_scale=1.0, stats=None, gn=None):
-    """segs: list of (act bf16 NHWC, packed weight, taps).  Returns the output tensor."""
+def run_conv(segs, N, H, W, cout, bias=None, residual=None, res_mode=0, out_mode=0, out_scale=1.0, stats=None, gn=None, in_gn=None):
+    """segs: list of (act bf16 NHWC, packed weight, taps).  Returns the output tensor.
+    in_gn = (ab fp32 [N, C, 2], silu, [channel offset of each segment or None]): fused GroupNorm apply on the operand path."""
     d = ConvDesc()
     d.N, d.H, d.W = N, H, W
     cout_pad = pad_rows(cout)
@@ -73,6 +74,12 @@ def run_conv(segs, N, H, W, cout, bias=None, residual=None, res_mode=0, out_mode
         d.gn_x0, d.gn_C0, d.gn_silu = x0.data_ptr(), x0.shape[-1], int(silu)
         d.gn_x1 = x1.data_ptr() if x1 is not None else None
         d.gn_ab, d.gn_red = ab.data_ptr(), red.data_ptr()
+    if in_gn is not None:
+        ab, silu, offs = in_gn
+        for i, off in enumerate(offs):
+            if off is not None:
+                d.in_ab[i] = ab.data_ptr() + off * 8
+        d.in_ab_C, d.in_silu = ab.shape[1], int(silu)
     plan = ctypes.c_void_p()
     check(lib.kdip_conv_plan_create(ctypes.byref(d), ctypes.byref(plan)))
     try:

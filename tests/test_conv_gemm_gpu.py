@@ -242,6 +242,79 @@ def test_conv_halo_pipeline(case, pair, monkeypatch):
     assert torch.allclose(stats[..., 1], (got * got).sum((2, 3)), rtol=1e-3, atol=3e-2)
 
 
+XF_CASES = [
+    # N, H, W, C0, C1 (second concatenated source), Cout, silu, extra raw 1x1 skip segment, residual
+    (1, 4, 128, 64, 0, 64, 1, 0, 0),
+    (2, 8, 256, 128, 0, 128, 1, 0, 1),     # two column blocks per row (left / right image edges in different tiles), identity skip
+    (3, 6, 128, 128, 64, 128, 1, 0, 0),    # concatenated input = two 3x3 K-segments, odd number of row pairs (single CTAs)
+    (2, 4, 128, 64, 0, 192, 0, 0, 0),      # no activation (attention-style norm), N tile 64 x 3
+    (2, 8, 128, 128, 0, 128, 1, 1, 0),     # conv2 of a channel-changing ResBlock: normalised 3x3 segment + raw 1x1 skip segment
+]
+
+
+@pytest.mark.parametrize("case", XF_CASES, ids=lambda c: "x".join(map(str, c)))
+@pytest.mark.parametrize("pair", ["1", "0"])
+def test_conv_fused_groupnorm_apply(case, pair, monkeypatch):
+    """GroupNorm affine (+SiLU) applied to the landed rows in shared memory (kdip_conv_desc.in_ab) vs the separate gn_apply pass
+    followed by the same conv: the operand bits are the same, so the outputs must be identical; and vs torch on the fp32 formula."""
+    from kdip._lib import check, lib, ptr, stream_ptr
+    from gpu_util import pack_weight, run_conv, to_nchw_f32, to_nhwc_bf16, relerr
+    monkeypatch.setenv("KDIP_HALO_PAIR", pair)
+    N, H, W, C0, C1, Co, silu, skip, res = case
+    C = C0 + C1
+    x0 = _mk(N, C0, H, W, 1) * 1.5 + 0.3
+    x1 = _mk(N, C1, H, W, 2) if C1 else None
+    g = torch.Generator(device="cuda").manual_seed(3)
+    ab = torch.stack([1 + 0.3 * torch.randn(N, C, device="cuda", generator=g), 0.5 * torch.randn(N, C, device="cuda", generator=g)], -1).contiguous()
+    w = _mk(Co, C, 3, 3, 4) / (C * 9) ** 0.5
+    b = _mk(1, Co, 1, 1, 5).flatten()
+    s0, s1 = to_nhwc_bf16(x0), (to_nhwc_bf16(x1) if C1 else None)
+    # unfused: gn_apply -> normalised bf16 tensor -> conv
+    a = torch.empty(N, H, W, C, dtype=torch.bfloat16, device="cuda")
+    check(lib.kdip_layer_gn_apply(ptr(s0), C0, ptr(s1), C1, N, H, W, ptr(ab), silu, 0, ptr(a), stream_ptr()))
+    extra, extra_ref = [], 0
+    if skip:
+        xs = _mk(N, 64, H, W, 7)
+        ws = _mk(Co, 64, 1, 1, 8) / 8
+        extra = [(to_nhwc_bf16(xs), pack_weight(ws)[0], 1)]
+        extra_ref = F.conv2d(_bf(xs), _bf(ws))
+    r = to_nhwc_bf16(_mk(N, Co, H, W, 9)) if res else None
+    kw = dict(bias=b, residual=r, res_mode=1 if res else 0)
+    st_a, st_b = torch.zeros(N, Co, 2, device="cuda"), torch.zeros(N, Co, 2, device="cuda")
+    ref = run_conv([(a, pack_weight(w)[0], 9)] + extra, N, H, W, Co, stats=st_a, **kw)
+    if C1:
+        segs = [(s0, pack_weight(w, ci_off=0, ci_sub=C0)[0], 9), (s1, pack_weight(w, ci_off=C0, ci_sub=C1)[0], 9)]
+        offs = [0, C0]
+    else:
+        segs, offs = [(s0, pack_weight(w)[0], 9)], [0]
+    got = run_conv(segs + extra, N, H, W, Co, stats=st_b, in_gn=(ab, silu, offs + [None] * len(extra)), **kw)
+    assert torch.isfinite(got.float()).all()
+    if C1 == 0:
+        assert torch.equal(got, ref), f"fused != unfused: max diff {(got.float() - ref.float()).abs().max().item()}"
+        assert torch.equal(st_a, st_b) or torch.allclose(st_a, st_b, rtol=1e-5, atol=1e-3)   # atomics: order only
+    else:   # two K-segments accumulate in a different order than one concatenated segment
+        assert relerr(got, ref) < 1.0 / 256
+    # torch: fp32 affine (+SiLU), rounded to bf16 like the stored operand, zero padding applied AFTER the normalisation
+    xin = torch.cat([_bf(x0)] + ([_bf(x1)] if C1 else []), 1)
+    u = ab[:, :, 0, None, None] * xin + ab[:, :, 1, None, None]
+    u = _bf(F.silu(u) if silu else u)
+    t = F.conv2d(u, _bf(w), b, padding=1) + extra_ref
+    if res:
+        t = t + to_nchw_f32(r)
+    e = relerr(to_nchw_f32(got), t)
+    print(f"fused GN-apply conv {case} pair={pair}: rel err vs torch {e:.3e}")
+    assert e < TOL
+
+
+def test_conv_fused_groupnorm_apply_needs_halo():
+    """in_ab on a shape the row-tile pipeline does not cover is refused (never silently ignored)."""
+    from gpu_util import pack_weight, run_conv, to_nhwc_bf16
+    x, w = _mk(1, 64, 16, 16, 1), _mk(64, 64, 3, 3, 2)
+    ab = torch.ones(1, 64, 2, device="cuda")
+    with pytest.raises(ValueError):
+        run_conv([(to_nhwc_bf16(x), pack_weight(w)[0], 9)], 1, 16, 16, 64, in_gn=(ab, 1, [0]))
+
+
 def test_conv_halo_matches_tile_pipeline():
     """Same conv through the halo pipeline (default) and (KDIP_CONV_HALO=0) the 8x16-tile pipeline: identical up to fp32 summation order."""
     import os

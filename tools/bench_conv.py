@@ -29,6 +29,9 @@ for (H, Ci, Co, taps, res) in SHAPES:
     if res:
         d.residual, d.res_mode = r.data_ptr(), 1
     d.out, d.out_mode, d.out_scale = out.data_ptr(), 0, 1.0
+    if os.environ.get("KDIP_BENCH_XF") == "1" and taps == 9 and H >= 128:   # fused GroupNorm apply on the operand path
+        ab = torch.stack([1 + 0.1 * torch.randn(B, Ci, device="cuda"), 0.1 * torch.randn(B, Ci, device="cuda")], -1).contiguous()
+        d.in_ab[0], d.in_ab_C, d.in_silu = ab.data_ptr(), Ci, 1
     plan = ctypes.c_void_p()
     check(lib.kdip_conv_plan_create(ctypes.byref(d), ctypes.byref(plan)))
     for _ in range(3):
