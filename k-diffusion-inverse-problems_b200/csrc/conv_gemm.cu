@@ -22,6 +22,7 @@
 //   input gradient), 2x2 avg-pool / nearest-up skip paths (unet.py:190-197).
 #include <stdlib.h>
 
+#define KDIP_MBAR_WAIT_QUIET
 #include "kdip_common.cuh"
 
 namespace kdip {
@@ -43,7 +44,8 @@ static constexpr int kMaxStages = 8;
 static constexpr int kHaloPix = 130;
 static constexpr int kHaloRowBytes = kHaloPix * 128;    // 16640 B landed by TMA
 static constexpr int kHaloSlot = 17 * 1024;             // slot stride (keeps every slot 1024-byte aligned)
-static constexpr int kHaloSlots = 6;                    // four rows of the current chunk + two of the next
+static constexpr int kHaloSlots = 6;                    // default ring: four rows of the current chunk + two of the next
+static constexpr int kMaxHaloSlots = 8;                 // ConvParams.halo_slots (KDIP_HALO_SLOTS) may deepen the ring
 
 struct ConvParams {
   CUtensorMap mapA[3];
@@ -55,6 +57,7 @@ struct ConvParams {
   int pair;             // 1: CTA pairs (cta_group::2, M = 256 per pair, B split across the two CTAs)
   int mt;               // pixel tiles per work item (1 or 2): mt = 2 shares every weight stage between two M=128 accumulators
   int halo;             // 1: halo pipeline (see kHaloPix)
+  int halo_slots;       // activation-row slots of the ring (kHaloSlots .. kMaxHaloSlots)
   int halo_bo;          // 1: descriptors carry the matrix base offset (probe only; wrong on B200, see conv_plan_build)
   int ws;               // 1: the two tiles of a work item share the weight operand through the tensor core's collector (tcgen05.mma.ws)
   int dbg;              // timing experiments only (KDIP_CONV_DBG): 1 = no operand loads / waits, 2 = epilogue releases TMEM without reading or storing,
@@ -130,10 +133,10 @@ __device__ __forceinline__ int work_to_tile(const ConvParams& p, int work, int r
 }
 
 // register budgets of the 640-thread variant (setmaxnreg per warpgroup): the CTA starts with 640 x 96 registers;
-// control warps 56, two epilogue warpgroups 144, two transform warpgroups 64: (56 + 2 x 144 + 2 x 64) x 128 = 60416 <= 61440
-__device__ __forceinline__ void setmaxnreg_dec_56() { asm volatile("setmaxnreg.dec.sync.aligned.u32 56;" ::: "memory"); }
-__device__ __forceinline__ void setmaxnreg_dec_64() { asm volatile("setmaxnreg.dec.sync.aligned.u32 64;" ::: "memory"); }
-__device__ __forceinline__ void setmaxnreg_inc_144() { asm volatile("setmaxnreg.inc.sync.aligned.u32 144;" ::: "memory"); }
+// control warps 48, two epilogue warpgroups 144, two transform warpgroups 72: (48 + 2 x 144 + 2 x 72) x 128 = 61440
+__device__ __forceinline__ void setmaxnreg_ctl() { asm volatile("setmaxnreg.dec.sync.aligned.u32 48;" ::: "memory"); }
+__device__ __forceinline__ void setmaxnreg_xf() { asm volatile("setmaxnreg.dec.sync.aligned.u32 72;" ::: "memory"); }
+__device__ __forceinline__ void setmaxnreg_epi() { asm volatile("setmaxnreg.inc.sync.aligned.u32 144;" ::: "memory"); }
 
 // kXf (halo pipeline only): eight more warps (two warpgroups taking alternate rows) apply the GroupNorm affine + SiLU of the conv's input (nn.py:17-19, unet.py:237-257) to the
 // activation rows IN shared memory, between the TMA landing and the MMAs - the normalised tensor never exists in HBM.
@@ -152,7 +155,8 @@ __global__ void __launch_bounds__(kXf ? kXfThreads : kThreads, 1) conv_gemm_kern
   const int work0 = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int work_stride = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   // halo mode: [kHaloSlots activation-row slots][num_stages weight stages of BN x 128 B]
-  uint8_t* b_ring = smem + kHaloSlots * kHaloSlot;
+  const int nslots = p.halo_slots;
+  uint8_t* b_ring = smem + nslots * kHaloSlot;
   const int b_stage_bytes = p.b_rows * 128;
   uint8_t* staging = kHalo ? b_ring + p.num_stages * b_stage_bytes : smem + p.num_stages * stage_bytes;   // [2][128 rows][128 B], TMA-store source
   uint8_t* res_stage = staging + (p.tma_epilogue ? kStagingBytes : 0);        // residual tile, same layout
@@ -166,8 +170,8 @@ __global__ void __launch_bounds__(kXf ? kXfThreads : kThreads, 1) conv_gemm_kern
   uint64_t* res_empty_bar = res_full_bar + 1;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_empty_bar + 1);
   uint64_t* a_full_bar = res_empty_bar + 2;            // halo mode: activation-row slots
-  uint64_t* a_empty_bar = a_full_bar + kHaloSlots;
-  uint64_t* a_ready_bar = a_empty_bar + kHaloSlots;    // kXf: rows transformed (4 warps per CTA arrive; on the leader for pairs)
+  uint64_t* a_empty_bar = a_full_bar + kMaxHaloSlots;
+  uint64_t* a_ready_bar = a_empty_bar + kMaxHaloSlots;    // kXf: rows transformed (4 warps per CTA arrive; on the leader for pairs)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -195,7 +199,7 @@ __global__ void __launch_bounds__(kXf ? kXfThreads : kThreads, 1) conv_gemm_kern
     mbar_init(res_full_bar, 1);
     mbar_init(res_empty_bar, kEpiThreads);
     if (kHalo) {
-      for (int s = 0; s < kHaloSlots; ++s) {
+      for (int s = 0; s < nslots; ++s) {
         // pair: one arrive.expect_tx per CTA, both on the leader's barrier; kXf: every CTA's rows land on its own barrier
         mbar_init(&a_full_bar[s], (kPair && !kXf) ? 2 : 1);
         mbar_init(&a_empty_bar[s], 1);
@@ -219,7 +223,7 @@ __global__ void __launch_bounds__(kXf ? kXfThreads : kThreads, 1) conv_gemm_kern
   // kXf: every warpgroup sets its register budget at the top of its own role branch (ptxas allocates per region; a budget set in
   // code that all roles share afterwards would cap every role at the smallest one)
   if (warp < 4) {
-  if (kXf) setmaxnreg_dec_56();
+  if (kXf) setmaxnreg_ctl();
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (kHalo) {
@@ -245,7 +249,7 @@ __global__ void __launch_bounds__(kXf ? kXfThreads : kThreads, 1) conv_gemm_kern
                   tma_load_4d(smem + slot * kHaloSlot, &p.mapA[s], &a_full_bar[slot], ch * kBlockK, t.x0 - 1, ybase + r, t.n0);
                 }
                 __syncwarp();
-                if (++slot == kHaloSlots) { slot = 0; ph ^= 1; }
+                if (++slot == nslots) { slot = 0; ph ^= 1; }
               }
             }
           }
@@ -311,7 +315,7 @@ __global__ void __launch_bounds__(kXf ? kXfThreads : kThreads, 1) conv_gemm_kern
               uint32_t rp[4];
               for (int r = 0; r < nrows; ++r) {
                 rs[r] = aslot; rp[r] = aph;
-                if (++aslot == kHaloSlots) { aslot = 0; aph ^= 1; }
+                if (++aslot == nslots) { aslot = 0; aph ^= 1; }
               }
               const int ndy = k3 ? 3 : 1;
               for (int dyi = 0; dyi < ndy; ++dyi) {
@@ -473,7 +477,7 @@ __global__ void __launch_bounds__(kXf ? kXfThreads : kThreads, 1) conv_gemm_kern
     }
   }
   } else if (kXf && warp >= 12) {
-    setmaxnreg_dec_64();
+    setmaxnreg_xf();
     // ===================== operand transform: act(A x + B) on the landed rows, in place =====================
     // Thread tt owns the logical 16-byte chunk j = tt & 7 (channels 8j .. 8j+7 of the 64-channel block) of the pixels (tt >> 3) + 16 i;
     // the 128B swizzle keeps it in physical chunk j ^ (pixel & 7), the same for all of them.  Pixels outside the image were
@@ -508,7 +512,7 @@ __global__ void __launch_bounds__(kXf ? kXfThreads : kThreads, 1) conv_gemm_kern
             }
             for (int r = 0; r < nrows; ++r, ++rowctr) {
               if ((int)(rowctr & 1u) != wg) {      // the other warpgroup's row
-                if (++slot == kHaloSlots) { slot = 0; ph ^= 1; }
+                if (++slot == nslots) { slot = 0; ph ^= 1; }
                 continue;
               }
               mbar_wait(&a_full_bar[slot], ph);
@@ -553,14 +557,14 @@ __global__ void __launch_bounds__(kXf ? kXfThreads : kThreads, 1) conv_gemm_kern
               if (lane == 0) {
                 if (kPair) mbar_arrive_cluster(leader_addr(&a_ready_bar[slot])); else mbar_arrive(&a_ready_bar[slot]);
               }
-              if (++slot == kHaloSlots) { slot = 0; ph ^= 1; }
+              if (++slot == nslots) { slot = 0; ph ^= 1; }
             }
           }
         }
       }
     }
   } else if (warp >= 4 && warp < 12 && (kXf || p.tma_epilogue)) {
-    if (kXf) setmaxnreg_inc_144();
+    if (kXf) setmaxnreg_epi();
     // ===================== epilogue (TMA store): 8 warps; warp (q, g) owns TMEM lanes [32q, 32q+32) x slab g =====================
     const int q = warp & 3;
     const int g = (warp - 4) >> 2;
@@ -998,6 +1002,7 @@ int conv_plan_build(const kdip_conv_desc* d, ConvPlan* plan) {
     if (d->in_ab[s] != nullptr) xf = true;
   }
   p.xf_C = d->in_ab_C; p.xf_silu = d->in_silu;
+
   if (xf) {
     KDIP_REQUIRE(p.halo, KDIP_ESHAPE, "conv: the fused GroupNorm apply (in_ab) needs the halo pipeline: 3x3 first segment, W a multiple of 128, even H, bf16 NHWC output in 64-channel slabs");
     KDIP_REQUIRE(d->in_ab_C > 0 && d->in_ab_C % 8 == 0, KDIP_EINVAL, "conv: in_ab_C=%d must be the (positive, multiple of 8) channel count of the (A, B) table", d->in_ab_C);
@@ -1146,7 +1151,11 @@ int conv_plan_build(const kdip_conv_desc* d, ConvPlan* plan) {
     if (d->gn_red != nullptr) p.res_slab_bytes = kSlabBytes;
   }
   const int stage_bytes = p.halo ? p.b_rows * 128 : p.mt * kABytes + p.b_rows * 128;
-  const int fixed = p.halo ? kHaloSlots * kHaloSlot : 0;
+  // the transform stage adds latency between a row's landing and its first MMA: one more slot of look-ahead (measured: UNet forward
+  // 13.48 -> 13.36 ms at B=32; the 128-pixel level 157 -> 126 us per 128->128 conv); the plain pipeline gains nothing from it
+  p.halo_slots = xf ? kHaloSlots + 1 : kHaloSlots;
+  if (const char* e = getenv("KDIP_HALO_SLOTS")) { const int v = atoi(e); if (v >= 5 && v <= kMaxHaloSlots) p.halo_slots = v; }
+  const int fixed = p.halo ? p.halo_slots * kHaloSlot : 0;
   const int budget = 227 * 1024 - extra - 1024 /*align slack*/ - 512 - fixed;
   int stages = budget / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
