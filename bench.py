@@ -527,5 +527,25 @@ def main():
         dist.destroy_process_group()
 
 
+def _trap_report():
+    """After a failed run: the conv pipeline's host-mapped wait-timeout record (include/kdip.h: kdip_conv_trap_read), if any."""
+    try:
+        import ctypes
+        from kdip._lib import lib
+        buf = (ctypes.c_uint * 64)()
+        n = lib.kdip_conv_trap_read(buf, 64)
+        if n:
+            recs = [tuple(buf[4 + 4 * i: 8 + 4 * i]) for i in range(min(n, 15))]
+            print("[bench] conv_gemm wait timeouts: %d; (line, block, thread|parity<<16, barrier) = %s" % (n, recs), file=sys.stderr)
+        else:
+            print("[bench] no conv_gemm wait-timeout record", file=sys.stderr)
+    except Exception as e:                                                   # noqa: BLE001
+        print("[bench] trap record unavailable: %r" % (e,), file=sys.stderr)
+
+
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except BaseException:
+        _trap_report()
+        raise

@@ -36,6 +36,11 @@ unsigned long long kdip_launch_count(void);
 /* A caller that replays a captured CUDA graph of library calls bypasses the library's own launch path: it reports the kernel
  * nodes of each replay here (the count kdip_launch_count advanced by while the graph was captured). */
 void kdip_launch_count_add(size_t n);
+/* Diagnostics: a conv_gemm_kernel wait that times out (a pipeline-protocol bug; the kernel then traps and the context is lost)
+ * first leaves a record in host-mapped memory.  Copies up to n (<= 64) words: out[0] = number of timed-out waits, then from
+ * out[4] on four words per wait (source line in csrc/conv_gemm.cu, block, thread | parity << 16, barrier shared-memory address).
+ * Returns out[0]; 0 = no record.  Usable after the CUDA context has failed. */
+int kdip_conv_trap_read(unsigned int* out, int n);
 /* Device sanity: returns KDIP_OK when the current device is sm_100 (B200); fills sm_count if non-null. */
 int kdip_device_check(int* sm_count);
 

@@ -27,6 +27,30 @@
 
 namespace kdip {
 
+// A protocol bug must be diagnosable from the host: a wait that times out leaves (source line, block, thread, parity, barrier
+// address) in a host-mapped record before it traps (the context is dead afterwards, mapped host memory is not).  Read with
+// kdip_conv_trap_read.  No printf: the control warps run on a 48-register budget and cannot afford its call frame.
+static __device__ unsigned int* g_trap_rec = nullptr;     // [0] = number of records, then 4 words per record (up to 15)
+static unsigned int* g_trap_host = nullptr;
+__device__ __forceinline__ void mbar_wait_line(uint64_t* bar, uint32_t parity, uint32_t line) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 26)) {
+      unsigned int* rec = g_trap_rec;
+      if (rec != nullptr) {
+        const unsigned int i = atomicAdd_system(rec, 1u);
+        if (i < 15u) {
+          volatile unsigned int* r = rec + 4 + 4 * i;
+          r[0] = line; r[1] = blockIdx.x; r[2] = threadIdx.x | (parity << 16); r[3] = smem_u32(bar);
+        }
+        __threadfence_system();
+      }
+      __trap();
+    }
+  }
+}
+#define mbar_wait(bar, parity) mbar_wait_line(bar, parity, (uint32_t)__LINE__)
+
 static constexpr int kBlockM = 128;
 static constexpr int kBlockK = 64;                      // bf16 elements = 128 bytes = one swizzle row
 static constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KiB
@@ -61,7 +85,8 @@ struct ConvParams {
   int halo_bo;          // 1: descriptors carry the matrix base offset (probe only; wrong on B200, see conv_plan_build)
   int ws;               // 1: the two tiles of a work item share the weight operand through the tensor core's collector (tcgen05.mma.ws)
   int dbg;              // timing experiments only (KDIP_CONV_DBG): 1 = no operand loads / waits, 2 = epilogue releases TMEM without reading or storing,
-                        // 4 = operand-transform warps only hand the rows over, 8 = they copy the rows through registers without the math
+                        // 4 = operand-transform warps only hand the rows over, 8 = they copy the rows through registers without the math,
+                        // 16 = transform warpgroups wait only for their own rows (the protocol bug fixed in round 2, kept for the regression experiment)
   uint32_t res_slab_bytes;   // bytes TMA lands per 64-channel slab of the skip / GroupNorm-source tile
   int b_rows;           // weight rows each CTA loads per k-block: BN (single) or BN/2 (pair)
   int total_work;       // persistent-loop trip count: tiles (single) or pair tiles (pair)
@@ -511,11 +536,17 @@ __global__ void __launch_bounds__(kXf ? kXfThreads : kThreads, 1) conv_gemm_kern
               }
             }
             for (int r = 0; r < nrows; ++r, ++rowctr) {
-              if ((int)(rowctr & 1u) != wg) {      // the other warpgroup's row
+              // Every warpgroup observes EVERY phase of every slot's barrier, also for the rows the other one transforms: with an
+              // odd ring depth a slot alternates between the two warpgroups, a group that only waited for its own rows would
+              // test a parity two phases old, and a late TMA of the row in between (rows land out of order under L2 misses)
+              // let that wait pass on the previous contents of the slot - a double transform, a_ready counts off by four, and
+              // eventually a pipeline that never completes (seen once in ~9000 evaluations as a trapped wait).
+              const bool mine = (int)(rowctr & 1u) == wg;
+              if (mine || !(p.dbg & 16)) mbar_wait(&a_full_bar[slot], ph);   // dbg 16: the old protocol (regression experiments only)
+              if (!mine) {                         // the other warpgroup's row
                 if (++slot == nslots) { slot = 0; ph ^= 1; }
                 continue;
               }
-              mbar_wait(&a_full_bar[slot], ph);
               const int y = ybase + r;
               if (abp != nullptr && y >= 0 && y < p.H && !(p.dbg & 4)) {
                 uint8_t* row = smem + slot * kHaloSlot + col;
@@ -914,6 +945,16 @@ static void set_smem_attr() {
   cudaFuncSetAttribute(conv_gemm_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   cudaFuncSetAttribute(conv_gemm_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   cudaFuncSetAttribute(conv_gemm_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  // host-mapped trap record (mbar_wait_line); failing to get one only loses the diagnostics
+  if (cudaHostAlloc(reinterpret_cast<void**>(&g_trap_host), 64 * sizeof(unsigned int), cudaHostAllocMapped) == cudaSuccess) {
+    memset(g_trap_host, 0, 64 * sizeof(unsigned int));
+    unsigned int* dptr = nullptr;
+    if (cudaHostGetDevicePointer(reinterpret_cast<void**>(&dptr), g_trap_host, 0) == cudaSuccess)
+      cudaMemcpyToSymbol(g_trap_rec, &dptr, sizeof(dptr));
+  } else {
+    g_trap_host = nullptr;
+  }
+  cudaGetLastError();
   attr_set = true;
 }
 
@@ -1231,3 +1272,9 @@ extern "C" int kdip_conv_plan_run(const kdip_conv_plan* p, kdip_stream_t s) {
   return kdip::conv_plan_launch(&p->plan, (cudaStream_t)s);
 }
 extern "C" void kdip_conv_plan_destroy(kdip_conv_plan* p) { delete p; }
+extern "C" int kdip_conv_trap_read(unsigned int* out, int n) {
+  if (kdip::g_trap_host == nullptr || out == nullptr) return 0;
+  const int cnt = (int)kdip::g_trap_host[0];
+  for (int i = 0; i < n && i < 64; ++i) out[i] = kdip::g_trap_host[i];
+  return cnt;
+}

@@ -306,6 +306,49 @@ def test_conv_fused_groupnorm_apply(case, pair, monkeypatch):
     assert e < TOL
 
 
+@pytest.mark.parametrize("pair", ["1", "0"])
+def test_conv_fused_groupnorm_apply_repeatable(pair, monkeypatch):
+    """Pipeline-protocol regression (ring of 7 row slots shared by two transform warpgroups): many work items per CTA, hundreds of
+    launches with a cache-thrashing copy in between so the rows land out of order - every output must be bit-identical to the first
+    (a row transformed twice or consumed early changes bits; a lost barrier phase traps)."""
+    import ctypes
+    from kdip._lib import ConvDesc, check, lib, ptr, stream_ptr
+    from gpu_util import pack_weight, to_nhwc_bf16
+    monkeypatch.setenv("KDIP_HALO_PAIR", pair)
+    N, H, W, C, Co = 12, 256, 256, 128, 128
+    x = to_nhwc_bf16(_mk(N, C, H, W, 1) * 1.5 + 0.3)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    ab = torch.stack([1 + 0.3 * torch.randn(N, C, device="cuda", generator=g), 0.5 * torch.randn(N, C, device="cuda", generator=g)], -1).contiguous()
+    wp = pack_weight(_mk(Co, C, 3, 3, 4) / (C * 9) ** 0.5)[0]
+    outs = [torch.empty(N, H, W, Co, dtype=torch.bfloat16, device="cuda") for _ in range(2)]
+    plans = []
+    for o in outs:
+        d = ConvDesc()
+        d.N, d.H, d.W, d.Cout_pad, d.Cout, d.nseg = N, H, W, Co, Co, 1
+        d.seg[0].act, d.seg[0].C, d.seg[0].wgt, d.seg[0].taps = x.data_ptr(), C, wp.data_ptr(), 9
+        d.out, d.out_mode, d.out_scale = o.data_ptr(), 0, 1.0
+        d.in_ab[0], d.in_ab_C, d.in_silu = ab.data_ptr(), C, 1
+        pl = ctypes.c_void_p()
+        check(lib.kdip_conv_plan_create(ctypes.byref(d), ctypes.byref(pl)))
+        plans.append(pl)
+    try:
+        check(lib.kdip_conv_plan_run(plans[0], stream_ptr()))
+        ref = outs[0].clone()
+        thrash = torch.empty(96 << 20, dtype=torch.uint8, device="cuda")
+        bad = torch.zeros((), dtype=torch.int64, device="cuda")
+        for it in range(300):
+            if it % 3 == 0:
+                thrash.add_(1)                      # evicts x from L2: the next launch's rows come from HBM
+            k = it & 1
+            check(lib.kdip_conv_plan_run(plans[k], stream_ptr()))
+            bad += (outs[k] != ref).sum()
+        torch.cuda.synchronize()
+        assert int(bad.item()) == 0, f"{int(bad.item())} output elements changed between identical launches"
+    finally:
+        for pl in plans:
+            lib.kdip_conv_plan_destroy(pl)
+
+
 def test_conv_fused_groupnorm_apply_needs_halo():
     """in_ab on a shape the row-tile pipeline does not cover is refused (never silently ignored)."""
     from gpu_util import pack_weight, run_conv, to_nhwc_bf16
