@@ -72,7 +72,7 @@ extern "C" int kdip_layer_time_embed(const float* t, int N, int mc, const float*
 }
 extern "C" int kdip_layer_emb_proj(const float* semb, int N, int ted, const float* wall, const float* ball, int R, float* out,
                                    kdip_stream_t s) {
-  return launch_emb_proj(semb, N, ted, wall, ball, R, out, (cudaStream_t)s);
+  return launch_emb_proj(semb, nullptr, N, ted, wall, ball, R, out, (cudaStream_t)s);
 }
 extern "C" int kdip_layer_attention_fwd(const void* qkv, int N, int T, int heads, void* out, float* lse, kdip_stream_t s) {
   return launch_attention_fwd((const bf16*)qkv, N, T, heads, 64, (bf16*)out, lse, (cudaStream_t)s);

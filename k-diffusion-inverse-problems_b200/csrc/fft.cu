@@ -242,4 +242,25 @@ int launch_cols(const float2* in, float2* out, int planes, int S, const SpecOp& 
   return KDIP_OK;
 }
 
+int launch_spec_filter(const float* x, float* out, int planes, int S, const SpecOp& op, float alpha, const float* mul, float beta,
+                       const float* add, float2* specA, float2* specB, cudaStream_t s) {
+  // Measured on B200 (tools/time_fft.py, one application, us): planes 3 / 12 / 24 / 48 / 72 / 96 / 192: fused 18.7 / 19.4 / 23.8 / 42.4 /
+  // 58.6 / 64.8 / 125.5, three passes 29.2 / 29.0 / 29.8 / 37.4 / 48.4 / 62.3 / 116.1.  One cluster of 8 CTAs per plane: 37 clusters are
+  // co-resident, so up to one wave of planes the single launch wins (latency-bound regime: configs[0], B <= 12); beyond it both run
+  // at ~1 instruction per clock per SM (sync- and latency-bound register FFTs, profiles/r2_ncu_fft.txt) and the three passes, whose
+  // CTAs are independent, pack the SMs slightly better.  KDIP_FFT_FUSED=1 / 0 forces one or the other.
+  const int fused_mode = getenv("KDIP_FFT_FUSED") ? atoi(getenv("KDIP_FFT_FUSED")) : -1;
+  const bool fused_on = !getenv("KDIP_FFT_RADIX2") && (fused_mode == 1 || (fused_mode < 0 && planes <= 36));
+  if (S == 256 && fused_on && (op.mode == SPEC_MULT || op.mode == SPEC_DIV_CONJ)) {
+    int rc = check_fft_size(S, planes);
+    if (rc) return rc;
+    return launch_spec_filter_256(x, out, planes, op, alpha, mul, beta, add, s);
+  }
+  int rc = launch_rows_r2c(x, specA, planes, S, s);
+  if (rc) return rc;
+  rc = launch_cols(specA, specB, planes, S, op, s);
+  if (rc) return rc;
+  return launch_rows_c2r(specB, out, planes, S, alpha, mul, beta, add, s);
+}
+
 }  // namespace kdip

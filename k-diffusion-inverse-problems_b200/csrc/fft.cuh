@@ -34,5 +34,13 @@ int launch_cols(const float2* in, float2* out, int planes, int S, const SpecOp& 
 int launch_rows_r2c_256(const float* x, float2* out, int planes, cudaStream_t s);
 int launch_rows_c2r_256(const float2* in, float* out, int planes, float alpha, const float* mul, float beta, const float* add, cudaStream_t s);
 int launch_cols_256(const float2* in, float2* out, int planes, const SpecOp& op, cudaStream_t s);
+// S = 256, SPEC_MULT / SPEC_DIV_CONJ: the whole application out = alpha * IFFT2(op(FFT2 x)) * mul + beta * add in ONE launch
+// (8-CTA cluster per plane, spectrum resident in distributed shared memory)
+int launch_spec_filter_256(const float* x, float* out, int planes, const SpecOp& op, float alpha, const float* mul, float beta,
+                           const float* add, cudaStream_t s);
+// dispatcher: the fused kernel when it applies (KDIP_FFT_FUSED=0 keeps the three passes), else rows_r2c -> cols(op) -> rows_c2r
+// through the two caller-provided half-spectrum buffers
+int launch_spec_filter(const float* x, float* out, int planes, int S, const SpecOp& op, float alpha, const float* mul, float beta,
+                       const float* add, float2* specA, float2* specB, cudaStream_t s);
 
 }  // namespace kdip

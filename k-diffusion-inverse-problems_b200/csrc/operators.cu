@@ -489,14 +489,10 @@ static int get_ws(const kdip_op* op, int B, void* ws, size_t ws_bytes, OpWs* w) 
 static int blur_apply(const kdip_op* op, const OpWs& w, const float* x, int conj, float* out, int planes, float sign,
                       const float* mul, float beta, const float* add, cudaStream_t st) {
   const int S = op->S;
-  int rc = launch_rows_r2c(x, w.specA, planes, S, st);
-  if (rc) return rc;
   SpecOp so;
   memset(&so, 0, sizeof(so));
   so.mode = SPEC_MULT; so.planes_per_image = 3; so.otf = op->otf; so.conj_otf = conj;
-  rc = launch_cols(w.specA, w.specB, planes, S, so, st);
-  if (rc) return rc;
-  return launch_rows_c2r(w.specB, out, planes, S, sign / ((float)S * (float)S), mul, beta, add, st);
+  return launch_spec_filter(x, out, planes, S, so, sign / ((float)S * (float)S), mul, beta, add, w.specA, w.specB, st);
 }
 
 static int resizer_forward(const kdip_op* op, const OpWs& w, const float* x, const float* noise, float sigma, float* y, int planes,
@@ -641,12 +637,8 @@ extern "C" int kdip_mat_closed(const kdip_op* op, const float* y, const float* x
     // ifft2( fft2(y - A x0) / (sigma_s^2 + theta |FB|^2) * conj(FB) )          condition.py:357
     rc = residual(op, w, y, x0, w.full[0], B, true, st);
     if (rc) return rc;
-    rc = launch_rows_r2c(w.full[0], w.specA, planes, S, st);
-    if (rc) return rc;
     so.mode = SPEC_DIV_CONJ; so.sigma_s2 = sig * sig;
-    rc = launch_cols(w.specA, w.specB, planes, S, so, st);
-    if (rc) return rc;
-    return launch_rows_c2r(w.specB, mat, planes, S, 1.f / ((float)S * (float)S), nullptr, 0.f, nullptr, st);
+    return launch_spec_filter(w.full[0], mat, planes, S, so, 1.f / ((float)S * (float)S), nullptr, 0.f, nullptr, w.specA, w.specB, st);
   }
   // SR: ifft2( conj(FB) * tile( fft2(y - down(A x0)) / (sigma_s^2 + theta invW) ) )       condition.py:404-410
   if (sig < 1e-2f) sig = 1e-2f;

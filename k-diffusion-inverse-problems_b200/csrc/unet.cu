@@ -554,9 +554,9 @@ static int build_launch_plan(kdip_unet* u, int N, void* ws, size_t ws_bytes, siz
     int n = N, R = u->R;
     F.push_back([=](cudaStream_t s) {
       KDIP_CUDA(cudaMemsetAsync(uu->stats_base, 0, uu->stats_bytes, s));
-      return launch_time_embed(uu->io_t, n, mc, tw1, tb1, tw2, tb2, semb, s);
+      return launch_time_embed(uu->io_t, n, mc, tw1, tb1, tw2, tb2, semb, s, true);
     });
-    F.push_back([=](cudaStream_t s) { return launch_emb_proj(semb, n, ted, uu->wall, uu->ball, R, film, s); });
+    F.push_back([=](cudaStream_t s) { return launch_emb_proj(semb, uu->io_t, n, ted, uu->wall, uu->ball, R, film, s); });
   }
 
   struct SavedRes { Act src0, src1, h1, out; float *ab1, *mr1, *ab2, *mr2; int Hin, Win, Ho, Wo; bool two; };

@@ -933,13 +933,48 @@ int launch_fold_taps(const bf16* src, int rows_pad, int CO, int cols, int dst_ro
 // ---------------------------------------------------------------------------------------------------------------------
 // timestep embedding
 // ---------------------------------------------------------------------------------------------------------------------
+// Images of one sampler call share their timestep (k_diffusion/sampling.py passes sigma * ones): an image whose t equals an
+// earlier image's skips the MLP here, and emb_proj copies that image's projected row.  The rows of a layer are independent dot
+// products: eight per warp at a time, so a warp has 8 x (K / 32) loads in flight instead of one row's (the kernel is one L2
+// round trip per step long: 90 -> ~10 us).
+__device__ __forceinline__ int first_equal_t(const float* __restrict__ t, int n) {
+  const float tv = t[n];
+  for (int i = 0; i < n; ++i)
+    if (t[i] == tv) return i;
+  return n;
+}
+template <int K_PER_LANE_MAX>
+__device__ __forceinline__ void mlp_rows8(const float* __restrict__ w, const float* __restrict__ b, const float* __restrict__ in, int K, int rows,
+                                          float* __restrict__ out_rows) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int j0 = warp * 8; j0 < rows; j0 += nw * 8) {
+    float acc[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) acc[r] = 0.f;
+    for (int k = lane; k < K; k += 32) {
+      const float v = in[k];
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+        if (j0 + r < rows) acc[r] = fmaf(__ldg(w + (size_t)(j0 + r) * K + k), v, acc[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const float a = warp_sum(acc[r]);
+      if (lane == 0 && j0 + r < rows) out_rows[j0 + r] = silu_f(a + b[j0 + r]);
+    }
+  }
+}
 __global__ void time_embed_kernel(const float* __restrict__ t, int mc, const float* __restrict__ w1, const float* __restrict__ b1,
-                                  const float* __restrict__ w2, const float* __restrict__ b2, float* __restrict__ semb) {
+                                  const float* __restrict__ w2, const float* __restrict__ b2, float* __restrict__ semb, int dedupe) {
   extern __shared__ float sm[];  // e0[mc] | h1[4mc]
+  __shared__ int s_first;
   float* e0 = sm;
   float* h1 = sm + mc;
   const int n = blockIdx.x;
   const int ted = 4 * mc, half = mc / 2;
+  if (threadIdx.x == 0) s_first = dedupe ? first_equal_t(t, n) : n;
+  __syncthreads();
+  if (s_first != n) return;
   const float tv = t[n];
   for (int k = threadIdx.x; k < mc; k += blockDim.x) {
     const int kk = k < half ? k : k - half;
@@ -948,30 +983,19 @@ __global__ void time_embed_kernel(const float* __restrict__ t, int mc, const flo
     e0[k] = k < half ? cosf(a) : sinf(a);
   }
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int j = warp; j < ted; j += nw) {
-    float acc = 0.f;
-    for (int k = lane; k < mc; k += 32) acc += __ldg(w1 + (size_t)j * mc + k) * e0[k];
-    acc = warp_sum(acc);
-    if (lane == 0) h1[j] = silu_f(acc + b1[j]);
-  }
+  mlp_rows8<4>(w1, b1, e0, mc, ted, h1);
   __syncthreads();
-  for (int j = warp; j < ted; j += nw) {
-    float acc = 0.f;
-    for (int k = lane; k < ted; k += 32) acc += __ldg(w2 + (size_t)j * ted + k) * h1[k];
-    acc = warp_sum(acc);
-    if (lane == 0) semb[(size_t)n * ted + j] = silu_f(acc + b2[j]);
-  }
+  mlp_rows8<16>(w2, b2, h1, ted, ted, semb + (size_t)n * ted);
 }
 int launch_time_embed(const float* t, int N, int mc, const float* w1, const float* b1, const float* w2, const float* b2,
-                      float* semb, cudaStream_t s) {
+                      float* semb, cudaStream_t s, bool dedupe) {
   KDIP_REQUIRE(mc % 2 == 0, KDIP_ESHAPE, "time_embed: model_channels must be even");
-  time_embed_kernel<<<N, 512, (size_t)5 * mc * sizeof(float), s>>>(t, mc, w1, b1, w2, b2, semb);
+  time_embed_kernel<<<N, 512, (size_t)5 * mc * sizeof(float), s>>>(t, mc, w1, b1, w2, b2, semb, dedupe ? 1 : 0);
   KDIP_LAUNCH_CHECK();
   return KDIP_OK;
 }
 
-__global__ void emb_proj_kernel(const float* __restrict__ semb, int N, int ted, const float* __restrict__ wall,
+__global__ void emb_proj_kernel(const float* __restrict__ semb, const float* __restrict__ t, int N, int ted, const float* __restrict__ wall,
                                 const float* __restrict__ ball, int R, float* __restrict__ out) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -982,6 +1006,18 @@ __global__ void emb_proj_kernel(const float* __restrict__ semb, int N, int ted, 
   for (int i = 0; i < 32; ++i) wreg[i] = (i < per) ? __ldg(wall + (size_t)r * ted + i * 32 + lane) : 0.f;
   const float b = ball[r];
   for (int n = 0; n < N; ++n) {
+    // first image with this image's timestep (time_embed_kernel filled semb only for those)
+    const float tn = t ? __ldg(t + n) : 0.f;
+    int m = n;
+    for (int base = 0; t != nullptr && base < n; base += 32) {
+      const int i = base + lane;
+      const unsigned bal = __ballot_sync(0xffffffffu, i < n && __ldg(t + i) == tn);
+      if (bal) { m = base + __ffs(bal) - 1; break; }
+    }
+    if (m != n) {
+      if (lane == 0) out[(size_t)n * R + r] = out[(size_t)m * R + r];     // written by this same lane in an earlier iteration
+      continue;
+    }
     float acc = 0.f;
 #pragma unroll
     for (int i = 0; i < 32; ++i)
@@ -990,9 +1026,9 @@ __global__ void emb_proj_kernel(const float* __restrict__ semb, int N, int ted, 
     if (lane == 0) out[(size_t)n * R + r] = acc + b;
   }
 }
-int launch_emb_proj(const float* semb, int N, int ted, const float* wall, const float* ball, int R, float* out, cudaStream_t s) {
+int launch_emb_proj(const float* semb, const float* t, int N, int ted, const float* wall, const float* ball, int R, float* out, cudaStream_t s) {
   KDIP_REQUIRE(ted % 32 == 0 && ted <= 1024, KDIP_ESHAPE, "emb_proj: time_embed_dim=%d unsupported", ted);
-  emb_proj_kernel<<<(R + 7) / 8, 256, 0, s>>>(semb, N, ted, wall, ball, R, out);
+  emb_proj_kernel<<<(R + 7) / 8, 256, 0, s>>>(semb, t, N, ted, wall, ball, R, out);
   KDIP_LAUNCH_CHECK();
   return KDIP_OK;
 }

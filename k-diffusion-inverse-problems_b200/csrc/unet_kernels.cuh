@@ -63,9 +63,11 @@ int launch_fold_taps(const bf16* src, int rows_pad, int CO, int cols, int dst_ro
 
 // timestep embedding (nn.py:103-121) + time_embed MLP (unet.py:473-477): semb[N][ted] = SiLU(W2 SiLU(W1 e(t) + b1) + b2)
 int launch_time_embed(const float* t, int N, int mc, const float* w1, const float* b1, const float* w2, const float* b2,
-                      float* semb, cudaStream_t s);
+                      float* semb, cudaStream_t s, bool dedupe = false);
 // all ResBlocks' emb_layers Linear at once: out[N][R] = Wall[R][ted] . semb[n] + ball[R]   (unet.py:199-205,246)
-int launch_emb_proj(const float* semb, int N, int ted, const float* wall, const float* ball, int R, float* out, cudaStream_t s);
+// dedupe (time_embed) / t != nullptr (emb_proj): an image whose timestep equals an earlier image's re-uses that image's row - the
+// two must be used together (time_embed then leaves the duplicate rows of semb unwritten)
+int launch_emb_proj(const float* semb, const float* t, int N, int ted, const float* wall, const float* ball, int R, float* out, cudaStream_t s);
 
 // QKVAttentionLegacy (unet.py:339-356).  qkv bf16 [N,T,3C], channel = head*3*ch + {q,k,v}*ch + c.
 // out bf16 [N,T,C] (channel = head*ch + c); lse fp32 [N,heads,T] (log-sum-exp of the scaled scores, for the backward).

@@ -170,3 +170,25 @@ def test_full_size_properties(name):
     m1 = op.handle.mat_closed(y1 + yv, x0, th)
     m2 = op.handle.mat_closed(y1 + 2 * yv, x0, th)
     assert rel(m2 - m0, 2 * (m1 - m0)) < 1e-4
+
+
+@pytest.mark.parametrize("B", [2, 14])
+@pytest.mark.parametrize("name", ["gaussian_blur", "motion_blur"])
+def test_fused_spectral_filter_matches_three_passes(name, B, monkeypatch):
+    """The single-launch cluster kernel (spec_filter_256_kernel: spectrum resident in distributed shared memory, Nyquist column
+    packed into column 0) against the three-pass path and the oracle, for A, A^T and the closed-form mat with per-image theta;
+    B = 14 (42 planes) runs more clusters than are co-resident."""
+    op, ref = make_op(name, 256), make_ref(name, 256)
+    g = torch.Generator().manual_seed(11)
+    x = (torch.rand(B, 3, 256, 256, generator=g) * 2 - 1)
+    yv = torch.randn(B, 3, 256, 256, generator=g)
+    th = (torch.rand(B, generator=g) * 0.5 + 0.01)
+    outs = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("KDIP_FFT_FUSED", mode)
+        h = op.handle
+        outs[mode] = [h.forward(x.cuda(), None), h.transpose(yv.cuda()), h.mat_closed(yv.cuda(), x.cuda(), th.cuda())]
+    for a, b in zip(outs["1"], outs["0"]):
+        assert rel(a, b) < 2e-6, rel(a, b)
+    assert rel(outs["1"][0][:2], ref.forward(x[:2], noiseless=True)) < 2e-5
+    assert rel(outs["1"][1][:2], ref.transpose(yv[:2])) < 2e-5

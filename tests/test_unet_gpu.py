@@ -60,6 +60,14 @@ def test_tiny_unet_batch_independence_and_scale(tiny_engine):
         one = eng.forward((x[b:b + 1] * sc[b]).contiguous(), t[b:b + 1])
         e_max, _ = _errs(one, full[b:b + 1])
         assert e_max < 3e-2, (b, e_max)   # bf16 network: different tile/stat accumulation order only
+    # repeated timesteps (what a sampler call passes): the timestep MLP runs once per distinct t and its projected rows are copied;
+    # mixed with distinct ones, in any order
+    t2 = torch.tensor([400, 5, 400, 400, 5]).cuda()
+    full2 = eng.forward(x, t2, x_scale=sc).clone()
+    for b in range(5):
+        one = eng.forward((x[b:b + 1] * sc[b]).contiguous(), t2[b:b + 1])
+        e_max, _ = _errs(one, full2[b:b + 1])
+        assert e_max < 3e-2, (b, e_max)
 
 
 def test_ffhq_unet_forward(golden_ffhq):
