@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(F_THREADS) rows_r2c_256_kernel(const float* __
   __shared__ float2 tw[256];
   extern __shared__ float2 tiles[];   // [16][F_TILE]
   constexpr int S = 256, Sh = 129;
-  make_tw256(tw);
+  make_tw256_kj(tw);
   const int f = threadIdx.x >> 4, j = threadIdx.x & 15;
   const size_t row0 = (size_t)blockIdx.x * 32;
   const float* ra = x + (row0 + 2 * f) * S;
@@ -104,8 +104,8 @@ __global__ void __launch_bounds__(F_THREADS) rows_r2c_256_kernel(const float* __
 #pragma unroll
   for (int n1 = 0; n1 < 16; ++n1) u[n1] = make_float2(__ldg(ra + 16 * n1 + j), __ldg(rb + 16 * n1 + j));
   float2* tile = tiles + f * F_TILE;
-  fft256<false>(u, j, tile, tw);
-  __syncthreads();
+  fft256<false, true>(u, j, tile, tw);
+  __syncwarp();
 #pragma unroll
   for (int k2 = 0; k2 < 16; ++k2) tile[j * F_LD + k2] = u[k2];       // Z[j + 16 k2] at [j][k2]
   __syncthreads();
@@ -133,20 +133,38 @@ __global__ void __launch_bounds__(F_THREADS) rows_c2r_256_kernel(const float2* _
   __shared__ float2 tw[256];
   extern __shared__ float2 tiles[];
   constexpr int S = 256, Sh = 129;
-  make_tw256(tw);
+  make_tw256_kj(tw);
   const size_t row0 = (size_t)blockIdx.x * 32;
-  // 16 iterations per thread, unrolled so that the 32 global loads of a thread are in flight together (the loop was latency-bound:
-  // one L2 round trip per iteration)
-#pragma unroll 8
-  for (int i = threadIdx.x; i < 16 * S; i += F_THREADS) {
-    const int t = i >> 8, k = i & 255;
-    const float2* pa = in + (row0 + 2 * t) * Sh;
-    const float2* pb = pa + Sh;
-    float2 xa, xb;
-    if (k < Sh) { xa = pa[k]; xb = pb[k]; }
-    else { xa = pa[S - k]; xa.y = -xa.y; xb = pb[S - k]; xb.y = -xb.y; }
-    // Z = Xa + i*Xb, element k = 16 n1 + n2 stored at [n2][n1]
-    tiles[t * F_TILE + (k & 15) * F_LD + (k >> 4)] = make_float2(xa.x - xb.y, xa.y + xb.x);
+  // Each bin of the half spectrum is read ONCE: half-warp task (t, d) loads bins k = 16 d + j of the rows 2t, 2t+1 (128-byte
+  // segments) and writes Z[k] = Xa + i Xb as well as its Hermitian image Z[S - k] = conj(Xa) + i conj(Xb); all sixteen loads of a
+  // thread are issued before the first use.  (The first version walked k = 0..255 and fetched every bin twice, 32 loads per
+  // thread at 100 registers: 63 % of its stall samples were L2 round trips.)
+  {
+    const int f = threadIdx.x >> 4, j = threadIdx.x & 15;
+    float2 xa[8], xb[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int task = f + 16 * q, t = task >> 3, d = task & 7;
+      const float2* pa = in + (row0 + 2 * t) * Sh + 16 * d + j;
+      xa[q] = pa[0];
+      xb[q] = pa[Sh];
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int task = f + 16 * q, t = task >> 3, d = task & 7;
+      const int k = 16 * d + j;
+      float2* tl = tiles + t * F_TILE;
+      tl[j * F_LD + d] = make_float2(xa[q].x - xb[q].y, xa[q].y + xb[q].x);      // element k = 16 n1 + n2 lives at [n2][n1]
+      if (k != 0) {
+        const int kc = S - k;
+        tl[(kc & 15) * F_LD + (kc >> 4)] = make_float2(xa[q].x + xb[q].y, xb[q].x - xa[q].y);
+      }
+    }
+    if (threadIdx.x < 16) {   // Nyquist bins
+      const float2* pa = in + (row0 + 2 * threadIdx.x) * Sh + 128;
+      const float2 a = pa[0], b = pa[Sh];
+      tiles[threadIdx.x * F_TILE + 0 * F_LD + 8] = make_float2(a.x - b.y, a.y + b.x);
+    }
   }
   __syncthreads();
   const int f = threadIdx.x >> 4, j = threadIdx.x & 15;
@@ -154,7 +172,7 @@ __global__ void __launch_bounds__(F_THREADS) rows_c2r_256_kernel(const float2* _
   float2 u[16];
 #pragma unroll
   for (int n1 = 0; n1 < 16; ++n1) u[n1] = tile[j * F_LD + n1];
-  fft256<true>(u, j, tile, tw);
+  fft256<true, true>(u, j, tile, tw);
   const size_t oa = (row0 + 2 * f) * S, ob = oa + S;
 #pragma unroll
   for (int k2 = 0; k2 < 16; ++k2) {
@@ -171,38 +189,53 @@ __global__ void __launch_bounds__(F_THREADS) rows_c2r_256_kernel(const float2* _
 // columns: 16 spectrum columns of one plane per CTA; thread (j, c): column c, member j of that column's 16-thread group
 // (tid = 16 j + c, so that a warp touches two 128-byte row segments of the [ky][kx] arrays)
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(F_THREADS) cols_256_kernel(const float2* __restrict__ in, float2* __restrict__ out, SpecOp op) {
+__global__ void __launch_bounds__(F_THREADS, 3) cols_256_kernel(const float2* __restrict__ in, float2* __restrict__ out, SpecOp op) {
   __shared__ float2 tw[256];
-  extern __shared__ float2 tiles[];
+  extern __shared__ float2 tiles[];         // [16][F_TILE] exchange tiles, then the parked OTF values [256][16]
   constexpr int S = 256, Sh = 129, G = 9;   // column groups per plane
+  float2* otf_s = tiles + 16 * F_TILE;
   make_tw256(tw);
   const int p = blockIdx.x / G, kx0 = (blockIdx.x - p * G) * 16;
   const int j = threadIdx.x >> 4, c = threadIdx.x & 15;
   const int kx = kx0 + c;
   const bool live = kx < Sh;
+  const bool use_otf = op.mode == SPEC_MULT || op.mode == SPEC_DIV_CONJ;
   const float2* src = in + (size_t)p * S * Sh + kx;
   float2* tile = tiles + c * F_TILE;
   float2 u[16];
+  // The sixteen OTF bins this thread will need after the forward transform (ky = j + 16 k2) are fetched together with its data and
+  // parked in shared memory (private slots: no synchronisation): inside the filter loop their L2 round trips serialised.
+  if (use_otf && live) {
+    float2 fb[16];
 #pragma unroll
-  for (int n1 = 0; n1 < 16; ++n1) u[n1] = live ? src[(size_t)(16 * n1 + j) * Sh] : make_float2(0.f, 0.f);
+    for (int k2 = 0; k2 < 16; ++k2) fb[k2] = __ldg(op.otf + (size_t)(j + 16 * k2) * Sh + kx);
+#pragma unroll
+    for (int n1 = 0; n1 < 16; ++n1) u[n1] = src[(size_t)(16 * n1 + j) * Sh];
+#pragma unroll
+    for (int k2 = 0; k2 < 16; ++k2) otf_s[(j + 16 * k2) * 16 + c] = fb[k2];
+  } else {
+#pragma unroll
+    for (int n1 = 0; n1 < 16; ++n1) u[n1] = live ? src[(size_t)(16 * n1 + j) * Sh] : make_float2(0.f, 0.f);
+  }
   fft256<false>(u, j, tile, tw);            // u[k2] = X[ky = j + 16 k2]
   if (op.mode != SPEC_FORWARD_ONLY) {
     const int img = p / op.planes_per_image;
     if (live) {
+      const float theta = (op.mode == SPEC_DIV_CONJ || op.mode == SPEC_DIV_TABLE) ? op.theta[img] : 0.f;
 #pragma unroll
       for (int k2 = 0; k2 < 16; ++k2) {
         const size_t sidx = (size_t)(j + 16 * k2) * Sh + kx;
         float2 v = u[k2];
         if (op.mode == SPEC_MULT) {
-          float2 m = op.otf[sidx];
+          float2 m = otf_s[(j + 16 * k2) * 16 + c];
           if (op.conj_otf) m.y = -m.y;
           v = c_mul(v, m);
         } else if (op.mode == SPEC_DIV_CONJ) {
-          const float2 fb = op.otf[sidx];
-          const float den = op.sigma_s2 + op.theta[img] * (fb.x * fb.x + fb.y * fb.y);
+          const float2 fb = otf_s[(j + 16 * k2) * 16 + c];
+          const float den = op.sigma_s2 + theta * (fb.x * fb.x + fb.y * fb.y);
           v = c_mul(make_float2(v.x / den, v.y / den), make_float2(fb.x, -fb.y));
         } else if (op.mode == SPEC_DIV_TABLE) {
-          const float den = op.sigma_s2 + op.theta[img] * op.table[sidx];
+          const float den = op.sigma_s2 + theta * op.table[sidx];
           v = make_float2(v.x / den, v.y / den);
         }
         u[k2] = v;
@@ -463,7 +496,13 @@ int launch_spec_filter_256(const float* x, float* out, int planes, const SpecOp&
   return KDIP_OK;
 }
 int launch_cols_256(const float2* in, float2* out, int planes, const SpecOp& op, cudaStream_t s) {
-  cols_256_kernel<<<(unsigned)(planes * 9), F_THREADS, kTilesBytes, s>>>(in, out, op);
+  static bool attr_set = false;
+  const size_t smem = kTilesBytes + (size_t)256 * 16 * sizeof(float2);
+  if (!attr_set) {
+    KDIP_CUDA(cudaFuncSetAttribute(cols_256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  cols_256_kernel<<<(unsigned)(planes * 9), F_THREADS, smem, s>>>(in, out, op);
   KDIP_LAUNCH_CHECK();
   return KDIP_OK;
 }
