@@ -208,10 +208,14 @@ __device__ __forceinline__ float block_sum(float v) {
 __global__ void __launch_bounds__(OP_THREADS) dot_partial_kernel(const float* __restrict__ a, const float* __restrict__ bvec,
                                                                   float* __restrict__ part, size_t n) {
   const size_t img = blockIdx.y;
-  const float* ap = a + img * n;
-  const float* bp = bvec ? bvec + img * n : ap;
+  const float4* ap = reinterpret_cast<const float4*>(a + img * n);
+  const float4* bp = bvec ? reinterpret_cast<const float4*>(bvec + img * n) : ap;
   float acc = 0.f;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) acc += ap[i] * bp[i];
+  const size_t n4 = n >> 2;       // n is a multiple of 4 (3 S^2, S >= 16); 16-byte loads, 4 elements per thread and trip
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 u = ap[i], v = bp[i];
+    acc += (u.x * v.x + u.y * v.y) + (u.z * v.z + u.w * v.w);
+  }
   acc = block_sum(acc);
   if (threadIdx.x == 0) part[img * CG_NBLK + blockIdx.x] = acc;
 }
@@ -237,11 +241,15 @@ __global__ void __launch_bounds__(OP_THREADS) cg_init_kernel(const float* __rest
                                                               float* __restrict__ part, size_t n) {
   const size_t img = blockIdx.y;
   float acc = 0.f;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const float v = r[img * n + i];
-    x[img * n + i] = 0.f;
-    p[img * n + i] = v;
-    acc += v * v;
+  const float4* r4 = reinterpret_cast<const float4*>(r + img * n);
+  float4* x4 = reinterpret_cast<float4*>(x + img * n);
+  float4* p4 = reinterpret_cast<float4*>(p + img * n);
+  const size_t n4 = n >> 2;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = r4[i];
+    x4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    p4[i] = v;
+    acc += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
   }
   acc = block_sum(acc);
   if (threadIdx.x == 0) part[img * CG_NBLK + blockIdx.x] = acc;
@@ -264,12 +272,19 @@ __global__ void __launch_bounds__(OP_THREADS) cg_update_kernel(float* __restrict
   float acc = 0.f;
   if (!st.done[cur][img]) {
     const float alpha = st.rho[cur][img] / sum_partials(part_pq, (int)img);
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-      const size_t o = img * n + i;
-      x[o] = x[o] + alpha * p[o];
-      const float rv = r[o] - alpha * q[o];
-      r[o] = rv;
-      acc += rv * rv;
+    float4* x4 = reinterpret_cast<float4*>(x + img * n);
+    float4* r4 = reinterpret_cast<float4*>(r + img * n);
+    const float4* p4 = reinterpret_cast<const float4*>(p + img * n);
+    const float4* q4 = reinterpret_cast<const float4*>(q + img * n);
+    const size_t n4 = n >> 2;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+      float4 xv = x4[i], rv = r4[i];
+      const float4 pv = p4[i], qv = q4[i];
+      xv.x = xv.x + alpha * pv.x; xv.y = xv.y + alpha * pv.y; xv.z = xv.z + alpha * pv.z; xv.w = xv.w + alpha * pv.w;
+      rv.x = rv.x - alpha * qv.x; rv.y = rv.y - alpha * qv.y; rv.z = rv.z - alpha * qv.z; rv.w = rv.w - alpha * qv.w;
+      x4[i] = xv;
+      r4[i] = rv;
+      acc += (rv.x * rv.x + rv.y * rv.y) + (rv.z * rv.z + rv.w * rv.w);
     }
   }
   acc = block_sum(acc);
@@ -291,9 +306,14 @@ __global__ void __launch_bounds__(OP_THREADS) cg_p_kernel(float* __restrict__ p,
     st.iters[img] += 1;
     st.done[nxt][img] = (rr < st.atol2[img]) ? 1 : 0;
   }
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const size_t o = img * n + i;
-    p[o] = r[o] + beta * p[o];
+  float4* p4 = reinterpret_cast<float4*>(p + img * n);
+  const float4* r4 = reinterpret_cast<const float4*>(r + img * n);
+  const size_t n4 = n >> 2;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 rv = r4[i];
+    float4 pv = p4[i];
+    pv.x = rv.x + beta * pv.x; pv.y = rv.y + beta * pv.y; pv.z = rv.z + beta * pv.z; pv.w = rv.w + beta * pv.w;
+    p4[i] = pv;
   }
 }
 // norm[b] = sqrt(sum partials)
