@@ -320,6 +320,10 @@ def guidance_roofline(cfg, operator, dev, B, pk):
         us = e0.elapsed_time(e1) * 1e3 / reps
         gbs = planes * B * PLANE / (us * 1e-6) / 1e9
         row = {"kernel": name, "us": us, "algorithmic_planes_per_image": planes, "GB/s": gbs, "frac": gbs / peak}
+        spectral = ("spectral" in name or "closed form" in name or "dps_grad" in name or "CG" in name) and operator.name != "inpainting"
+        # the FFT-based entries are bound by the register FFTs (instruction issue + L2 latency), not by HBM: their
+        # HBM fraction is reported for completeness, the instruction floor of one blur application at B = 32 is ~15 us
+        row["bound"] = "fp32 ALU / latency (register FFT), not HBM" if spectral else "hbm"
         if note:
             row["note"] = note
         rows.append(row)

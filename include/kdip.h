@@ -382,6 +382,19 @@ int kdip_guided_eval_run(kdip_unet* u, kdip_op* op, int guidance, const float* x
                          size_t ws_bytes, kdip_stream_t s);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * LPIPS building blocks - sample_condition_openai.py:46,161 (`lpips.LPIPS(net='vgg')`; the `lpips` package v0.1 is a third-party
+ * dependency, its published algorithm is restated in csrc/lpips.cu and oracle/lpips_ref.py).  The VGG16 convolutions go through
+ * kdip_conv_plan_* / kdip_layer_conv_small_cin; these are the kernels around them.  Activations are bf16 NHWC.
+ * ------------------------------------------------------------------------------------------------------------ */
+/* in-place ReLU over n bf16 elements (n a multiple of 8, 16-byte aligned) */
+int kdip_relu_bf16(void* x, size_t n, kdip_stream_t s);
+/* nn.MaxPool2d(2, 2): [N,H,W,C] -> [N,H/2,W/2,C] (even H, W; C a multiple of 8) */
+int kdip_maxpool2_bf16(const void* in, void* out, int N, int H, int W, int C, kdip_stream_t s);
+/* out[n] += mean_p sum_c w[c] (f0[n,p,c] / (|f0[n,p,:]| + 1e-10) - f1[n,p,c] / (|f1[n,p,:]| + 1e-10))^2   (out: fp64 [N], caller zeroes;
+ * lpips normalize_tensor + (diff)^2 + NetLinLayer 1x1 conv + spatial_average of one feature tap) */
+int kdip_lpips_layer(const void* f0, const void* f1, const float* w, int N, int HW, int C, double* out, kdip_stream_t s);
+
+/* ------------------------------------------------------------------------------------------------------------
  * UNet building blocks, exported for per-layer parity tests (tests/test_layers_gpu.py).  Activations are bf16 NHWC.
  * See csrc/unet_kernels.cuh for the full semantics of each argument.
  * ------------------------------------------------------------------------------------------------------------ */

@@ -689,9 +689,7 @@ static int apply_cov(const OpWs& w, int ot, const float* theta, const float* t_i
     return KDIP_OK;
   }
   if (ot == KDIP_OT_DWT) {
-    int rc = launch_dwt(t_in, theta, planes, tmp, planes, S, 0, st);
-    if (rc) return rc;
-    return launch_dwt(tmp, nullptr, 0, t_out, planes, S, 1, st);
+    return launch_dwt_cov(t_in, theta, planes, tmp, t_out, planes, S, st);
   }
   int rc = launch_dct(t_in, theta, B, tmp, B, S, 0, w.dct, st);
   if (rc) return rc;

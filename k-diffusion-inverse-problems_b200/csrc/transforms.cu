@@ -145,6 +145,119 @@ int launch_dwt(const float* x, const float* mul, int mul_planes, float* out, int
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// W diag(theta) W^T in ONE pass (S = 256): the posterior covariance applied in image space (condition/utils.py:146-163, used once
+// per CG iteration by condition.py:338,374,427).  A level-3 Haar transform only mixes pixels inside 8 x 8 blocks, so a CTA takes
+// an 8-row strip down the three levels, scales every coefficient by theta where it is produced, and comes straight back up:
+// each thread keeps the scaled details of the 2 x 2 blocks it analysed in registers and synthesises the same blocks on the way
+// up, only the approximations go through shared memory.  3 planes of traffic (x, theta, out) instead of the 5 of
+// dwt_fwd * theta -> dwt_inv, one launch instead of two; the arithmetic is the two kernels' (the theta product is rounded before
+// it is used, as when it went through memory), so the results are bit-identical.
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void haar_analyse(float x00, float x01, float x10, float x11, float& aa, float (&band)[3]) {
+  const float lo0 = (x00 + x10) * kInvSqrt2, lo1 = (x01 + x11) * kInvSqrt2;
+  const float hi0 = (x00 - x10) * kInvSqrt2, hi1 = (x01 - x11) * kInvSqrt2;
+  aa = (lo0 + lo1) * kInvSqrt2;
+  band[1] = (lo0 - lo1) * kInvSqrt2;   // ad
+  band[0] = (hi0 + hi1) * kInvSqrt2;   // da
+  band[2] = (hi0 - hi1) * kInvSqrt2;   // dd
+}
+__device__ __forceinline__ void haar_synthesise(float aa, const float (&band)[3], float& y00, float& y01, float& y10, float& y11) {
+  const float da = band[0], ad = band[1], dd = band[2];
+  const float lo0 = (aa + ad) * kInvSqrt2, lo1 = (aa - ad) * kInvSqrt2;
+  const float hi0 = (da + dd) * kInvSqrt2, hi1 = (da - dd) * kInvSqrt2;
+  y00 = (lo0 + hi0) * kInvSqrt2;
+  y01 = (lo1 + hi1) * kInvSqrt2;
+  y10 = (lo0 - hi0) * kInvSqrt2;
+  y11 = (lo1 - hi1) * kInvSqrt2;
+}
+__global__ void __launch_bounds__(256) dwt_cov_256_kernel(const float* x, const float* __restrict__ theta,
+                                                          float* out, int mul_planes, int swap) {   // x may alias out (strip-local)
+  constexpr int S = 256;
+  __shared__ __align__(16) float a0[8 * S];    // the strip: input, then output
+  __shared__ float a1[4 * (S / 2)];
+  __shared__ float a2[2 * (S / 4)];
+  const int p = blockIdx.x / (S / 8), b = blockIdx.x - p * (S / 8);
+  const float4* src = reinterpret_cast<const float4*>(x + ((size_t)p * S + 8 * b) * S);
+  for (int i = threadIdx.x; i < 8 * S / 4; i += 256) reinterpret_cast<float4*>(a0)[i] = src[i];
+  __syncthreads();
+  const float* th = theta + (size_t)(p % mul_planes) * S * S;
+  float d1[2][3], d2[3] = {0.f, 0.f, 0.f}, d3[3];
+  // level 1: 4 x 128 blocks, two per thread
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int i = threadIdx.x + 256 * k, r = i >> 7, c = i & 127;
+    float aa, band[3];
+    haar_analyse(a0[(2 * r) * S + 2 * c], a0[(2 * r) * S + 2 * c + 1], a0[(2 * r + 1) * S + 2 * c], a0[(2 * r + 1) * S + 2 * c + 1], aa, band);
+    const int row = 4 * b + r;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      int r0, c0;
+      band_offset(q, S / 2, swap, r0, c0);
+      d1[k][q] = __fmul_rn(band[q], th[(size_t)(r0 + row) * S + c0 + c]);
+    }
+    a1[r * (S / 2) + c] = aa;
+  }
+  __syncthreads();
+  // level 2: 2 x 64 blocks
+  const int r2 = threadIdx.x >> 6, c2 = threadIdx.x & 63;
+  if (threadIdx.x < 128) {
+    float aa, band[3];
+    haar_analyse(a1[(2 * r2) * (S / 2) + 2 * c2], a1[(2 * r2) * (S / 2) + 2 * c2 + 1], a1[(2 * r2 + 1) * (S / 2) + 2 * c2],
+                 a1[(2 * r2 + 1) * (S / 2) + 2 * c2 + 1], aa, band);
+    const int row = 2 * b + r2;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      int r0, c0;
+      band_offset(q, S / 4, swap, r0, c0);
+      d2[q] = __fmul_rn(band[q], th[(size_t)(r0 + row) * S + c0 + c2]);
+    }
+    a2[r2 * (S / 4) + c2] = aa;
+  }
+  __syncthreads();
+  // level 3: 1 x 32 blocks, down and straight back up (a thread's block of a2 is read and rewritten by that thread only)
+  if (threadIdx.x < 32) {
+    const int c = threadIdx.x;
+    float aa, band[3];
+    haar_analyse(a2[2 * c], a2[2 * c + 1], a2[(S / 4) + 2 * c], a2[(S / 4) + 2 * c + 1], aa, band);
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      int r0, c0;
+      band_offset(q, S / 8, swap, r0, c0);
+      d3[q] = __fmul_rn(band[q], th[(size_t)(r0 + b) * S + c0 + c]);
+    }
+    aa = __fmul_rn(aa, th[(size_t)b * S + c]);
+    haar_synthesise(aa, d3, a2[2 * c], a2[2 * c + 1], a2[(S / 4) + 2 * c], a2[(S / 4) + 2 * c + 1]);
+  }
+  __syncthreads();
+  if (threadIdx.x < 128)
+    haar_synthesise(a2[r2 * (S / 4) + c2], d2, a1[(2 * r2) * (S / 2) + 2 * c2], a1[(2 * r2) * (S / 2) + 2 * c2 + 1],
+                    a1[(2 * r2 + 1) * (S / 2) + 2 * c2], a1[(2 * r2 + 1) * (S / 2) + 2 * c2 + 1]);
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int i = threadIdx.x + 256 * k, r = i >> 7, c = i & 127;
+    haar_synthesise(a1[r * (S / 2) + c], d1[k], a0[(2 * r) * S + 2 * c], a0[(2 * r) * S + 2 * c + 1], a0[(2 * r + 1) * S + 2 * c],
+                    a0[(2 * r + 1) * S + 2 * c + 1]);
+  }
+  __syncthreads();
+  float4* dst = reinterpret_cast<float4*>(out + ((size_t)p * S + 8 * b) * S);
+  for (int i = threadIdx.x; i < 8 * S / 4; i += 256) dst[i] = reinterpret_cast<const float4*>(a0)[i];
+}
+
+// out = W (theta .* W^T x): the fused kernel at S = 256 (KDIP_DWT_FUSED=0: the two transforms through `tmp`)
+int launch_dwt_cov(const float* x, const float* theta, int theta_planes, float* tmp, float* out, int planes, int S, cudaStream_t s) {
+  const bool fused = S == 256 && !(getenv("KDIP_DWT_FUSED") && atoi(getenv("KDIP_DWT_FUSED")) == 0);
+  if (fused) {
+    dwt_cov_256_kernel<<<planes * (S / 8), 256, 0, s>>>(x, theta, out, theta_planes > 0 ? theta_planes : planes, dwt_layout_swap());
+    KDIP_LAUNCH_CHECK();
+    return KDIP_OK;
+  }
+  int rc = launch_dwt(x, theta, theta_planes, tmp, planes, S, 0, s);
+  if (rc) return rc;
+  return launch_dwt(tmp, nullptr, 0, out, planes, S, 1, s);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // DCT-II (orthonormal) as matrix products
 // ---------------------------------------------------------------------------------------------------------------------
 // Cm[k][n] = alpha_k cos(pi (2n+1) k / (2S))

@@ -192,3 +192,20 @@ def test_fused_spectral_filter_matches_three_passes(name, B, monkeypatch):
         assert rel(a, b) < 2e-6, rel(a, b)
     assert rel(outs["1"][0][:2], ref.forward(x[:2], noiseless=True)) < 2e-5
     assert rel(outs["1"][1][:2], ref.transpose(yv[:2])) < 2e-5
+
+
+def test_fused_dwt_covariance_matches_two_transforms(monkeypatch):
+    """W diag(theta) W^T in one pass (dwt_cov_256_kernel) vs forward * theta -> inverse: the CG solutions at 256x256 with a
+    DWT-domain theta map must be bit-identical (same arithmetic, same iteration counts)."""
+    op = make_op("gaussian_blur", 256)
+    B = 3
+    g = torch.Generator().manual_seed(21)
+    x0 = (torch.rand(B, 3, 256, 256, generator=g) * 2 - 1).cuda()
+    y = op.handle.forward(x0, torch.randn(B, 3, 256, 256, generator=g).cuda())
+    tmap = (torch.rand(B, 3, 256, 256, generator=g) * 0.05 + 1e-4).cuda()
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("KDIP_DWT_FUSED", mode)
+        res[mode] = (op.handle.mat_cg(y, x0, tmap, ot="dwt").clone(), list(op.handle.last_cg_iters))
+    assert res["1"][1] == res["0"][1] and max(res["1"][1]) > 3, res["1"][1]
+    assert torch.equal(res["1"][0], res["0"][0]), (res["1"][0] - res["0"][0]).abs().max().item()
