@@ -26,6 +26,9 @@ for fused in (0, 1):
     d.N, d.H, d.W, d.Cout_pad, d.Cout, d.nseg = B, H, H, Co, Co, 1
     d.seg[0].act, d.seg[0].C, d.seg[0].wgt, d.seg[0].taps = x.data_ptr(), Ci, w.data_ptr(), taps
     d.out, d.out_mode, d.out_scale = out.data_ptr(), 0, 1.0
+    if os.environ.get("KDIP_BENCH_XF") == "1":   # + the operand transform on the conv's input (dgrad conv1 of a two-source experiment)
+        abx = torch.stack([1 + 0.1 * torch.randn(B, Ci, device="cuda"), 0.1 * torch.randn(B, Ci, device="cuda")], -1).contiguous()
+        d.in_ab[0], d.in_ab_C, d.in_silu = abx.data_ptr(), Ci, 1
     if fused:
         d.gn_x0, d.gn_C0, d.gn_silu = gx0.data_ptr(), C0, 1
         d.gn_x1 = gx1.data_ptr() if two else None
