@@ -157,11 +157,21 @@ __device__ __forceinline__ int work_to_tile(const ConvParams& p, int work, int r
   return m * p.n_tiles + nt;
 }
 
-// register budgets of the 640-thread variant (setmaxnreg per warpgroup): the CTA starts with 640 x 96 registers;
-// control warps 48, two epilogue warpgroups 144, two transform warpgroups 72: (48 + 2 x 144 + 2 x 72) x 128 = 61440
-__device__ __forceinline__ void setmaxnreg_ctl() { asm volatile("setmaxnreg.dec.sync.aligned.u32 48;" ::: "memory"); }
-__device__ __forceinline__ void setmaxnreg_xf() { asm volatile("setmaxnreg.dec.sync.aligned.u32 72;" ::: "memory"); }
-__device__ __forceinline__ void setmaxnreg_epi() { asm volatile("setmaxnreg.inc.sync.aligned.u32 144;" ::: "memory"); }
+// register budgets of the 640-thread variant (setmaxnreg per warpgroup): the CTA starts with 640 x 96 = 61440 registers;
+// control warps 72, two epilogue warpgroups 136, two transform warpgroups 64: (72 + 2 x 136 + 2 x 64) x 128 = 60416
+// Measured (tools/experiments/r2e_xf_regs.sh, 3x3 128->128 at 256^2, B=32): 48/72/144 550 us, 64/72/136 543 us, 72/64/136 538 us - the
+// control warps (TMA producers, MMA issuer) are the ones that profit from registers; 40/56/160 and 48/64/152 were no better than 48/72/144.
+#ifndef KDIP_XF_REG_CTL
+#define KDIP_XF_REG_CTL 72
+#define KDIP_XF_REG_XF 64
+#define KDIP_XF_REG_EPI 136
+#endif
+#define KDIP_STR2(x) #x
+#define KDIP_STR(x) KDIP_STR2(x)
+static_assert(4 * KDIP_XF_REG_CTL + 8 * KDIP_XF_REG_XF + 8 * KDIP_XF_REG_EPI <= 20 * 96, "register budgets exceed the CTA's pool");
+__device__ __forceinline__ void setmaxnreg_ctl() { asm volatile("setmaxnreg.dec.sync.aligned.u32 " KDIP_STR(KDIP_XF_REG_CTL) ";" ::: "memory"); }
+__device__ __forceinline__ void setmaxnreg_xf() { asm volatile("setmaxnreg.dec.sync.aligned.u32 " KDIP_STR(KDIP_XF_REG_XF) ";" ::: "memory"); }
+__device__ __forceinline__ void setmaxnreg_epi() { asm volatile("setmaxnreg.inc.sync.aligned.u32 " KDIP_STR(KDIP_XF_REG_EPI) ";" ::: "memory"); }
 
 // kXf (halo pipeline only): eight more warps (two warpgroups taking alternate rows) apply the GroupNorm affine + SiLU of the conv's input (nn.py:17-19, unet.py:237-257) to the
 // activation rows IN shared memory, between the TMA landing and the MMAs - the normalised tensor never exists in HBM.
