@@ -1,6 +1,6 @@
 #!/bin/bash
 # register budgets of the 640-thread conv variant: control / transform / epilogue
-for cfg in "48 72 144" "64 72 136" "72 64 136" "88 72 128"; do
+for cfg in "72 64 136" "80 64 136" "96 64 128"; do
   set -- $cfg
   touch k-diffusion-inverse-problems_b200/csrc/conv_gemm.cu
   KDIP_NVCC_EXTRA="-DKDIP_XF_REG_CTL=$1 -DKDIP_XF_REG_XF=$2 -DKDIP_XF_REG_EPI=$3" bash k-diffusion-inverse-problems_b200/csrc/build.sh > /tmp/build.log 2>&1 || { echo "build failed $cfg"; tail -3 /tmp/build.log; continue; }
