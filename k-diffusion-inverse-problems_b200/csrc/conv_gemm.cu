@@ -336,11 +336,15 @@ __global__ void __launch_bounds__(kXf ? kXfThreads : kThreads, 1) conv_gemm_kern
         int aslot = 0, bst = 0, acc = 0;
         uint32_t aph = 0, bph = 0, acc_phase = 0;
         const uint32_t a_base = smem_u32(smem), b_base = smem_u32(b_ring);
+        // loop invariants of the plan, read once (left as p.x inside the elected block they were re-fetched from the constant bank
+        // for every batch of eight MMAs)
+        const uint32_t idesc = p.idesc, halo_bo = (uint32_t)p.halo_bo, bn_cols = (uint32_t)p.BN;
+        const int n_stages = p.num_stages, use_ws = p.ws, dbg1 = p.dbg & 1;
         auto commit = [](uint64_t* bar) { if (kPair) umma_commit_2sm(bar); else umma_commit(bar); };   // pair: arrives in both CTAs
         for (int work = work0; work < p.total_work; work += work_stride) {
           mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
           tc_fence_after();
-          const uint32_t d0 = tmem_base + (uint32_t)(acc * 2 * p.BN), d1 = d0 + (uint32_t)p.BN;
+          const uint32_t d0 = tmem_base + (uint32_t)acc * 2u * bn_cols, d1 = d0 + bn_cols;
           uint32_t accum = 0;
           for (int s = 0; s < p.nseg; ++s) {
             const bool k3 = p.seg_taps[s] == 9;
@@ -355,7 +359,7 @@ __global__ void __launch_bounds__(kXf ? kXfThreads : kThreads, 1) conv_gemm_kern
               const int ndy = k3 ? 3 : 1;
               for (int dyi = 0; dyi < ndy; ++dyi) {
                 // tile 0 (row y0) reads slot row dyi, tile 1 (row y0+1) reads slot row dyi+1
-                if (!(p.dbg & 1)) {
+                if (!dbg1) {
                   uint64_t* a_rdy = kXf ? a_ready_bar : a_full_bar;
                   if (dyi == 0) mbar_wait(&a_rdy[rs[0]], rp[0]);
                   mbar_wait(&a_rdy[rs[dyi + 1]], rp[dyi + 1]);
@@ -364,9 +368,9 @@ __global__ void __launch_bounds__(kXf ? kXfThreads : kThreads, 1) conv_gemm_kern
                 const int ndx = k3 ? 3 : 1;
                 for (int dxi = 0; dxi < ndx; ++dxi) {
                   const uint32_t roff = k3 ? (uint32_t)dxi : 1u;       // rows into the slot: dx + 1
-                  if (!(p.dbg & 1)) mbar_wait(&full_bar[bst], bph);
+                  if (!dbg1) mbar_wait(&full_bar[bst], bph);
                   tc_fence_after();
-                  const uint32_t bo = p.halo_bo ? roff : 0u;
+                  const uint32_t bo = halo_bo ? roff : 0u;
                   const uint64_t a0_desc = umma_desc_sw128_bo(a_base + rs[dyi] * kHaloSlot + roff * 128u, bo);
                   const uint64_t a1_desc = umma_desc_sw128_bo(a_base + rs[dyi + 1] * kHaloSlot + roff * 128u, bo);
                   const uint64_t b_desc = umma_desc_sw128(b_base + bst * b_stage_bytes);
@@ -375,21 +379,21 @@ __global__ void __launch_bounds__(kXf ? kXfThreads : kThreads, 1) conv_gemm_kern
                   for (int k = 0; k < kBlockK / 16; ++k) {
                     const uint32_t acc_k = (accum | (uint32_t)k) ? 1u : 0u;    // only the very first MMA of a work item overwrites
                     if (kPair) {
-                      umma_bf16_ss_2sm(d0, a0_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), p.idesc, acc_k);
-                      umma_bf16_ss_2sm(d1, a1_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), p.idesc, acc_k);
-                    } else if (p.ws) {
-                      umma_bf16_ss_ws_fill(d0, a0_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), p.idesc, acc_k);
-                      umma_bf16_ss_ws_lastuse(d1, a1_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), p.idesc, acc_k);
+                      umma_bf16_ss_2sm(d0, a0_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, acc_k);
+                      umma_bf16_ss_2sm(d1, a1_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, acc_k);
+                    } else if (use_ws) {
+                      umma_bf16_ss_ws_fill(d0, a0_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, acc_k);
+                      umma_bf16_ss_ws_lastuse(d1, a1_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, acc_k);
                     } else {
-                      umma_bf16_ss(d0, a0_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), p.idesc, acc_k);
-                      umma_bf16_ss(d1, a1_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), p.idesc, acc_k);
+                      umma_bf16_ss(d0, a0_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, acc_k);
+                      umma_bf16_ss(d1, a1_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, acc_k);
                     }
                   }
                   commit(&empty_bar[bst]);
                   }
                   __syncwarp();
                   accum = 1;
-                  if (++bst == p.num_stages) { bst = 0; bph ^= 1; }
+                  if (++bst == n_stages) { bst = 0; bph ^= 1; }
                 }
                 // rows that no later tap of this chunk reads go back to the producer once the MMAs above retire
                 if (elect_one_sync()) {
