@@ -505,7 +505,11 @@ def main():
                 "avg_launch_ms": pr["conv_ms"] / max(1, pr["conv_launches"]),
                 "algorithmic_flops_per_launch": pr["conv_flops"] / max(1, pr["conv_launches"]),
                 "conv_share_of_eval": pr["conv_ms"] / pr["total_ms"], "eval_ms": pr["total_ms"],
-                "how": "cudaEvent pairs around each launch of one UNet forward+VJP (B=%d) on the launching stream" % B}
+                "how": "one CUDA event between consecutive launches of one UNet forward+VJP (B=%d) on the launching stream (eager "
+                       "launches, right after the timed region)" % B,
+                "note": "since round 2 the conv launches of the 256- and 128-pixel levels also apply the GroupNorm affine + SiLU of their "
+                        "input on the operand path (16 launches): that work is charged to the conv kernel here, the separate pass it "
+                        "replaced was not"}
     unet_tf = value / n_gpus * cfg["n_evals"] * cfg["gf"] / 1e3
     line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",

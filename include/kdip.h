@@ -329,11 +329,12 @@ int kdip_unet_vjp(kdip_unet* u, const float* seed, int N, float* grad_x, void* w
 int kdip_unet_prepare(kdip_unet* u, int N, void* workspace, size_t ws_bytes);
 
 /* Instrumented forward + input-VJP: the same launch lists with a CUDA-event pair around every step, summed by class.
- * Used by bench.py for the live roofline of the dominant kernel (conv_gemm_kernel); synchronises the stream. */
+ * Used by bench.py for the live roofline of the dominant kernel (conv_gemm_kernel); synchronises the stream.  One CUDA event is
+ * recorded between consecutive launches (a step runs from the event before it to the event after it). */
 typedef struct {
   float conv_ms;        /* device time inside tcgen05 implicit-GEMM conv launches                        */
   float other_ms;       /* GroupNorm / attention / small-conv / embedding kernels                        */
-  float total_ms;       /* first launch to last (includes gaps)                                          */
+  float total_ms;       /* sum over the steps (= first launch to last, minus the two untimed flop-counting passes) */
   double conv_flops;    /* algorithmic FLOPs of those conv launches (2 x MAC, padded channels excluded)  */
   int conv_launches;
   int other_steps;

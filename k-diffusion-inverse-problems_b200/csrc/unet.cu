@@ -1111,17 +1111,22 @@ extern "C" int kdip_unet_profile(kdip_unet* u, const float* x, const float* x_sc
   cudaStream_t s = (cudaStream_t)stream;
   u->io_x = x; u->io_xscale = x_scale; u->io_t = t; u->io_out = out; u->io_cov = nullptr;
   u->io_seed = seed; u->io_grad = grad_x;
-  struct Rec { cudaEvent_t a, b; bool conv; double flops; };
+  // One event BETWEEN consecutive launches (the end of step i is the start of step i + 1), all created up front: a pair per step put
+  // two event records into every gap and inflated the per-launch times by ~20 us each (26.4 ms of "conv" against 22.8 ms in ncu).
+  struct Rec { bool conv; double flops; int e0, e1; };
   std::vector<Rec> recs;
+  const size_t n_steps = u->fwd_ops.size() + u->bwd_ops.size() + 2;
+  std::vector<cudaEvent_t> ev(n_steps + 3);
+  for (auto& e : ev) KDIP_CUDA(cudaEventCreate(&e));
+  int cur = 0;                                     // index of the most recently recorded event
+  KDIP_CUDA(cudaEventRecord(ev[0], s));
+  auto mark = [&]() -> int { KDIP_CUDA(cudaEventRecord(ev[cur + 1], s)); ++cur; return KDIP_OK; };
   auto timed = [&](bool is_conv, double flops, const std::function<int()>& fn) -> int {
-    Rec r;
-    r.conv = is_conv; r.flops = flops;
-    KDIP_CUDA(cudaEventCreate(&r.a));
-    KDIP_CUDA(cudaEventCreate(&r.b));
-    KDIP_CUDA(cudaEventRecord(r.a, s));
+    const int e0 = cur;
     int q = fn();
-    KDIP_CUDA(cudaEventRecord(r.b, s));
-    recs.push_back(r);
+    if (q != KDIP_OK) return q;
+    q = mark();
+    recs.push_back(Rec{is_conv, flops, e0, cur});
     return q;
   };
   double fl = 0.0;
@@ -1130,6 +1135,8 @@ extern "C" int kdip_unet_profile(kdip_unet* u, const float* x, const float* x_sc
     if (rc != KDIP_OK) return rc;
   }
   forward_tail(u, N, out, nullptr, s, &fl);   // compute flops first (plan cached on the second call)
+  rc = mark();                                // ... untimed: the next step starts after it
+  if (rc != KDIP_OK) return rc;
   rc = timed(true, fl, [&]() { return forward_tail(u, N, out, nullptr, s, nullptr); });
   if (rc != KDIP_OK) return rc;
   for (auto& op : u->bwd_ops) {
@@ -1137,17 +1144,19 @@ extern "C" int kdip_unet_profile(kdip_unet* u, const float* x, const float* x_sc
     if (rc != KDIP_OK) return rc;
   }
   vjp_tail(u, N, grad_x, s, &fl);
+  rc = mark();
+  if (rc != KDIP_OK) return rc;
   rc = timed(true, fl, [&]() { return vjp_tail(u, N, grad_x, s, nullptr); });
   if (rc != KDIP_OK) return rc;
   KDIP_CUDA(cudaStreamSynchronize(s));
   memset(prof, 0, sizeof(*prof));
   for (auto& r : recs) {
     float ms = 0.f;
-    cudaEventElapsedTime(&ms, r.a, r.b);
+    cudaEventElapsedTime(&ms, ev[r.e0], ev[r.e1]);
     if (r.conv) { prof->conv_ms += ms; prof->conv_flops += r.flops; prof->conv_launches++; }
     else { prof->other_ms += ms; prof->other_steps++; }
+    prof->total_ms += ms;
   }
-  cudaEventElapsedTime(&prof->total_ms, recs.front().a, recs.back().b);
-  for (auto& r : recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  for (auto& e : ev) cudaEventDestroy(e);
   return KDIP_OK;
 }
